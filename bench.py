@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: associations/sec of
+scorePairwiseConsistency() + solve() (BASELINE.json), measured the way the reference's own
+benchmark times the two calls (reference benchmarks/main.cpp:177-188).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+One "step" = one full pass of the hot path over one synthetic association problem:
+score the m x m consistency graph, then run the graduated projected-gradient solver.
+  value : m*K / device time, inputs (D1, D2, A, u0) already resident in HBM (clp_*_dev entry points)
+  e2e   : the same through the host-pointer C-ABI calls (pinned host buffers in, Solution out),
+          host<->device copies inside the timed region
+  roofline : solver kernel (the dominant launch): n_matvec * 4 m^2 algorithmic bytes / its CUDA-event
+             duration, against MEASURED_PEAKS.json's hbm_gbs
+  cpu_baseline / --impl reference : the CPU oracle (Eigen-free restatement of the reference; the
+             reference cannot be built offline -- no Eigen) on this box's host cores.
+Prints exactly ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "associations/sec (scorePairwiseConsistency+solve)"
+UNIT = "associations/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference, all host threads it can use
+# ------------------------------------------------------------------------------------------
+def oracle_step(prob, nthreads):
+    from oracle import clipper_oracle as orc
+    cfg = prob["cfg"]
+    o = orc.Oracle()
+    t0 = time.perf_counter()
+    if cfg["kind"] == "euclidean":
+        o.score_euclidean(prob["D1"], prob["D2"], prob["A"], sigma=cfg["sigma"], epsilon=cfg["epsilon"], nthreads=nthreads)
+    else:
+        o.score_pointnormal(prob["D1"], prob["D2"], prob["A"], sigp=cfg["sigp"], epsp=cfg["epsp"], sign=cfg["sign"],
+                            epsn=cfg["epsn"], nthreads=nthreads)
+    t1 = time.perf_counter()
+    s = o.solve(prob["u0"])
+    t2 = time.perf_counter()
+    return dict(t_score=t1 - t0, t_solve=t2 - t1, evals=int(s.n_evals), nodes=s.nodes.tolist(), score=float(s.score),
+                nnz=o.nnz(0))
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same metric/config, on the host cores.
+    The literal reference needs Eigen3 (absent, no network) -> the Eigen-free oracle port is timed:
+    scoring with OpenMP on all cores (reference default parallelize_=true, clipper.h:154),
+    solver single-threaded (the reference's solver has no threading, clipper.cpp:172-323)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from clipper_b200 import datagen
+    cores = cpu_cores()
+    full_m = datagen.CONFIGS[args.workload]["m"]
+    # budget: keep (K+W) steps within ~4 minutes; ~17 s per full c2 step on 8 x 2.1 GHz cores
+    est_full = 17.0 * (full_m / 20000.0) ** 2
+    budget = 240.0
+    m_s = full_m
+    if est_full * args.steps > budget:
+        m_s = int(max(2000, (full_m * (budget / (est_full * args.steps)) ** 0.5) // 1000 * 1000))
+    prob = datagen.config_problem(args.workload, m_s)
+    warm = datagen.config_problem(args.workload, min(2000, m_s))
+    for _ in range(args.warmup):
+        oracle_step(warm, cores)  # warm-up on a small instance (thread pool, page cache)
+    ts = []
+    t0 = time.perf_counter()
+    info = None
+    for _ in range(args.steps):
+        info = oracle_step(prob, cores)
+        ts.append(info["t_score"] + info["t_solve"])
+    total = time.perf_counter() - t0
+    value = m_s * args.steps / total
+    sample = "full %s problem, m=%d" % (args.workload, m_s) if m_s == full_m else \
+        "m=%d sample of %s (m=%d) to bound the run" % (m_s, args.workload, full_m)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: synthetic EuclideanDistance m=%d, 95%% outliers" % (args.workload, m_s),
+                   "t_score_s": info["t_score"], "t_solve_s": info["t_solve"], "evals": info["evals"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + "; oracle restatement (Eigen/MKL unavailable offline): scoring OpenMP x%d, "
+                                            "solver 1 thread like the reference; warm-up on m=%d" % (cores, min(2000, m_s))},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from clipper_b200 import _capi, datagen
+    import clipper_b200 as clipperpy
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world > 1:
+        from clipper_b200 import distributed as cdist
+        return cdist.run_bench(args, METRIC, UNIT)
+
+    L = _capi.load()
+    prob = datagen.config_problem(args.workload, args.m)
+    cfg = prob["cfg"]; m = cfg["m"]
+    assert cfg["kind"] == "euclidean"
+    ip = clipperpy.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = cfg["sigma"], cfg["epsilon"]
+    clip = clipperpy.CLIPPER(clipperpy.invariants.EuclideanDistance(ip), clipperpy.Params(), device=local_rank)
+    h = clip.handle
+    stream = torch.cuda.current_stream()
+    clip.set_stream(stream.cuda_stream)
+
+    # ---- inputs resident in HBM
+    D1 = torch.from_numpy(np.ascontiguousarray(prob["D1"].T)).to(dev)
+    D2 = torch.from_numpy(np.ascontiguousarray(prob["D2"].T)).to(dev)
+    A = torch.from_numpy(np.ascontiguousarray(prob["A"].T)).to(dev)
+    u0 = torch.from_numpy(prob["u0"]).to(dev)
+    u_out = torch.empty_like(u0)
+    nodes = np.zeros(m, np.int32)
+    sol = _capi.ClpSolution()
+    n1, n2 = D1.shape[0], D2.shape[0]
+
+    def step_dev():
+        _capi.check(h, L.clp_score_euclidean_dev(h, D1.data_ptr(), 3, n1, D2.data_ptr(), n2, A.data_ptr(), m,
+                                                 cfg["sigma"], cfg["epsilon"], 0.0))
+        _capi.check(h, L.clp_solve_dev(h, u0.data_ptr(), C.byref(sol), u_out.data_ptr(),
+                                       nodes.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    # ---- the same through the host-pointer API (pinned host buffers)
+    hD1 = torch.from_numpy(np.ascontiguousarray(prob["D1"].T)).pin_memory()
+    hD2 = torch.from_numpy(np.ascontiguousarray(prob["D2"].T)).pin_memory()
+    hA = torch.from_numpy(np.ascontiguousarray(prob["A"].T)).pin_memory()
+    hu0 = torch.from_numpy(prob["u0"]).pin_memory()
+    hu = torch.empty(m, dtype=torch.float64).pin_memory()
+    dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    ipt = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_int32))
+    sol_h = _capi.ClpSolution()
+
+    def step_host():
+        _capi.check(h, L.clp_score_euclidean(h, dp(hD1), 3, n1, dp(hD2), n2, ipt(hA), m, cfg["sigma"], cfg["epsilon"], 0.0))
+        _capi.check(h, L.clp_solve(h, dp(hu0), C.byref(sol_h), dp(hu), nodes.ctypes.data_as(C.POINTER(C.c_int32)), None))
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, clocks sampled meanwhile
+    sampler = ClockSampler(local_rank); sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, n_matvec, evals = [], [], []
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+        kernel_ms.append(sol.kernel_ms); n_matvec.append(sol.n_matvec); evals.append(sol.n_evals)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    value = m * args.steps / (dev_ms * 1e-3)
+    nodes_dev = nodes[: sol.n_nodes].tolist(); F_dev = sol.score
+
+    # ---- e2e: host buffers in, Solution out, copies inside the timed region (wall clock)
+    for _ in range(3):
+        step_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    e2e_value = m * args.steps / e2e_s
+    h2d = hD1.numel() * 8 + hD2.numel() * 8 + hA.numel() * 4 + m * 8
+    d2h = m * 8 + 256 + 32 + 32  # u + result header + two status blocks
+    assert nodes[: sol_h.n_nodes].tolist() == nodes_dev and sol_h.score == F_dev
+
+    # ---- roofline of the dominant kernel (the persistent solver): algorithmic bytes = n_matvec * 4 m^2
+    peak, peak_src = measured_peaks()
+    esz = 4
+    alg_bytes = float(np.mean(n_matvec)) * esz * m * m
+    kms = float(np.mean(kernel_ms))
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    # stand-alone Md.v pass (K2) for the ">= 40 % of HBM roofline on the mat-vec" target
+    v = torch.rand(m, dtype=torch.float64, device=dev); y = torch.empty_like(v)
+    ms_mv = C.c_double()
+    _capi.check(h, L.clp_matvec_dev(h, v.data_ptr(), 1.0, y.data_ptr(), None, None, 5, C.byref(ms_mv)))
+    _capi.check(h, L.clp_matvec_dev(h, v.data_ptr(), 1.0, y.data_ptr(), None, None, 50, C.byref(ms_mv)))
+    mv_gbs = (esz * m * m + 16 * m) / (ms_mv.value * 1e-3) / 1e9
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1): one full oracle step (~10-30 s)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = cpu_cores()
+        info = oracle_step(prob, cores)
+        cpu = {"value": m / (info["t_score"] + info["t_solve"]), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 full step of the same %s problem (m=%d): oracle restatement, scoring OpenMP x%d %.2f s, "
+                         "solver single-threaded %.2f s, %d evaluations; Eigen/MKL reference unbuildable offline"
+                         % (args.workload, m, cores, info["t_score"], info["t_solve"], info["evals"]),
+               "t_score_s": info["t_score"], "t_solve_s": info["t_solve"],
+               "same_inlier_set": sorted(info["nodes"]) == sorted(nodes_dev),
+               "rel_dF": abs(info["score"] - F_dev) / abs(info["score"])}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 (f32 affinity storage, fp64 vectors/accumulators/decisions)", "data": "synthetic",
+        "config": {"workload": "%s: synthetic EuclideanDistance m=%d, 95%% outliers, sigma=%g eps=%g"
+                               % (args.workload, m, cfg["sigma"], cfg["epsilon"]),
+                   "l2": "inputs larger than L2 (dense M = %.2f GB vs 126 MB L2)" % (esz * m * m / 1e9),
+                   "evals_per_solve": float(np.mean(evals)), "matvec_per_solve": float(np.mean(n_matvec)),
+                   "solver_kernel_ms": kms, "matvec_alone_gbs": mv_gbs, "matvec_alone_ms": ms_mv.value,
+                   "matvec_alone_frac": mv_gbs / peak, "F": F_dev, "n_nodes": len(nodes_dev)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "solver_kernel<float> (persistent; %d dense passes of M per launch)"
+                                                % int(round(np.mean(n_matvec))), "peak_source": peak_src},
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
+    ap.add_argument("--m", type=int, default=None, help="override the workload's m (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,704 @@
+// clp_capi.cu -- host side of the C-ABI declared in include/clipper_b200.h.
+//
+// One handle = one CUDA device + one stream + the dense M store + the solver workspace.
+// There is NO CPU implementation of the hot path in this library: every scoring / mat-vec /
+// solve call launches the sm_100a kernels of clp_kernels.cuh or fails with an error code.
+#include "clp_kernels.cuh"
+#include "clp_host_utils.h"
+#include "../../include/clipper_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#ifndef CLP_VERSION
+#define CLP_VERSION "0.1.0"
+#endif
+
+using namespace clp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+}  // namespace
+
+struct clp_handle_s {
+  int device = 0;
+  int storage = CLP_STORE_F32;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  clp_params prm;
+  std::string err;
+  int sm_count = 0;
+  int ctas_per_sm = 2;
+
+  // sharding (row block [row0,row0+rows) of the m x m matrix lives here)
+  int rank = 0, world = 1;
+
+  // problem
+  long long m = 0;
+  int row0 = 0, rows = 0, rows_pad = 0;
+  long long ld = 0;
+  bool has_matrix = false;
+  DevBuf Mbuf;
+  bool has_A = false;
+  bool A_host_valid = false;
+  std::vector<int32_t> A_host;  // column-major m x 2
+  DevBuf A_dev;                 // int32 [2m]
+  DevBuf E1, E2, D1dev, D2dev;
+
+  // solver workspace
+  DevBuf vecs;    // 8 x mpad doubles: U0 U1 G0 G1 MV0 MV1 CV0 CV1
+  DevBuf parts;   // partM | partC : 2 x NSEG x rows_pad
+  DevBuf small;   // segsum[kMaxSeg] | red[2][G][kRedVals]
+  DevBuf result;  // SolverOut (256 B) | u_final[mpad]
+  DevBuf u0dev;   // [mpad]
+  DevBuf ybuf;    // matvec scratch: v | y | Mv | Cv  (4 x mpad)
+  DevBuf sync;    // counter (u64) | error (int) | flags (int) | counts (2 x u64)
+  DevBuf panel;   // staging panels for get/set dense
+  DevBuf cscbuf;
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  Plan plan{};
+  long long mpad = 0;
+
+  size_t esize() const { return storage == CLP_STORE_F64 ? 8 : 4; }
+};
+
+namespace {
+
+int fail(clp_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CLP_CUDA(h, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? CLP_ERR_ALLOC : CLP_ERR_CUDA,      \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+inline long long round_up(long long x, long long q) { return (x + q - 1) / q * q; }
+
+int ensure_pinned(clp_handle h, size_t bytes) {
+  if (bytes <= h->pinned_cap) return CLP_OK;
+  if (h->pinned) { cudaFreeHost(h->pinned); h->pinned = nullptr; h->pinned_cap = 0; }
+  CLP_CUDA(h, cudaMallocHost(&h->pinned, bytes));
+  h->pinned_cap = bytes;
+  return CLP_OK;
+}
+
+// unsigned long long counter | int error | int flags | u64 counts[2]
+struct SyncBlock { unsigned long long counter; int error; int flags; unsigned long long counts[2]; };
+
+void shard_rows(long long m, int rank, int world, int* row0, int* rows) {
+  // row tiles of 32 are never split between shards
+  const long long tiles = (m + kRowTile - 1) / kRowTile;
+  const long long t0 = tiles * rank / world, t1 = tiles * (rank + 1) / world;
+  long long r0 = t0 * kRowTile, r1 = std::min<long long>(t1 * kRowTile, m);
+  if (r0 > m) r0 = m;
+  *row0 = (int)r0; *rows = (int)std::max<long long>(0, r1 - r0);
+}
+
+// choose the CTA / segment decomposition of the mat-vec for this problem size
+Plan make_plan(long long m, int rows_pad, int G) {
+  Plan p;
+  p.G = G;
+  int SG = 1;
+  const long long cols128 = (m + 127) / 128;
+  for (int cand : {8, 4, 2, 1}) {
+    if (G % cand == 0 && cand <= std::max<long long>(1, cols128)) { SG = cand; break; }
+  }
+  const long long nseg_min = (m + kSegMax - 1) / kSegMax;
+  long long NSEG = SG * std::max<long long>(1, (nseg_min + SG - 1) / SG);
+  long long W = round_up((m + NSEG - 1) / NSEG, 128);
+  if (W < 128) W = 128;
+  NSEG = std::max<long long>(SG, round_up((m + W - 1) / W, SG));
+  p.SG = SG; p.RG = G / SG; p.NSEG = (int)NSEG; p.W = (int)W; p.NRT = rows_pad / kRowTile;
+  return p;
+}
+
+// (re)allocate the matrix store for problem size m under the current shard config
+int ensure_matrix(clp_handle h, long long m) {
+  if (m <= 0) return fail(h, CLP_ERR_INVALID, "number of associations must be positive");
+  if (m > (long long)kMaxSeg * kSegMax) return fail(h, CLP_ERR_INVALID, "m exceeds the supported maximum (262144)");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  h->m = m;
+  shard_rows(m, h->rank, h->world, &h->row0, &h->rows);
+  h->rows_pad = (int)round_up(std::max(h->rows, 1), kRowTile);
+  h->ld = round_up(m, 128);
+  h->mpad = round_up(m, 128);
+  CLP_CUDA(h, h->Mbuf.ensure((size_t)h->rows_pad * (size_t)h->ld * h->esize()));
+  h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_per_sm);
+  // workspace
+  CLP_CUDA(h, h->vecs.ensure((size_t)8 * h->mpad * sizeof(double)));
+  CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
+  CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
+  CLP_CUDA(h, h->result.ensure(256 + (size_t)h->mpad * sizeof(double)));
+  CLP_CUDA(h, h->u0dev.ensure((size_t)h->mpad * sizeof(double)));
+  CLP_CUDA(h, h->ybuf.ensure((size_t)4 * h->mpad * sizeof(double)));
+  if (int rc = ensure_pinned(h, 256 + (size_t)h->mpad * sizeof(double))) return rc;
+  h->has_matrix = false;
+  return CLP_OK;
+}
+
+MatView mat_view(clp_handle h) {
+  MatView mv;
+  mv.M = h->Mbuf.p; mv.ld = h->ld; mv.m = (int)h->m; mv.row0 = h->row0; mv.rows = h->rows; mv.rows_pad = h->rows_pad;
+  return mv;
+}
+
+int reset_sync(clp_handle h) {
+  CLP_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sizeof(SyncBlock), h->stream));
+  return CLP_OK;
+}
+
+int read_sync(clp_handle h, SyncBlock* sb) {
+  CLP_CUDA(h, cudaMemcpyAsync(sb, h->sync.p, sizeof(SyncBlock), cudaMemcpyDeviceToHost, h->stream));
+  CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLP_OK;
+}
+
+template <typename T>
+int launch_score(clp_handle h, int kind, int d, const ScoreArgs& a) {
+  dim3 grid((unsigned)(h->ld / 128), (unsigned)(h->rows_pad / kRowTile));
+  if (kind == 1) score_tile_kernel<T, 1, 6><<<grid, kThreads, 0, h->stream>>>(a);
+  else if (d == 3) score_tile_kernel<T, 0, 3><<<grid, kThreads, 0, h->stream>>>(a);
+  else if (d == 2) score_tile_kernel<T, 0, 2><<<grid, kThreads, 0, h->stream>>>(a);
+  else score_tile_kernel<T, 0, 0><<<grid, kThreads, 0, h->stream>>>(a);
+  CLP_CUDA(h, cudaGetLastError());
+  return CLP_OK;
+}
+
+// common tail of the four scoring entry points: D1/D2/A already on the device
+int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long n1, const double* D2d,
+                    long long n2, const int32_t* Ad, long long m, double p0, double p1, double p2, double p3) {
+  if (int rc = ensure_matrix(h, m)) return rc;
+  CLP_CUDA(h, h->E1.ensure((size_t)m * d * sizeof(double)));
+  CLP_CUDA(h, h->E2.ensure((size_t)m * d * sizeof(double)));
+  if (int rc = reset_sync(h)) return rc;
+  SyncBlock* sb = h->sync.as<SyncBlock>();
+  const int tb = 256;
+  gather_endpoints_kernel<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(
+      D1d, D2d, Ad, Ad + m, (int)m, d, n1, n2, h->E1.as<double>(), h->E2.as<double>(), &sb->error);
+  CLP_CUDA(h, cudaGetLastError());
+  ScoreArgs a;
+  a.E1 = h->E1.as<double>(); a.E2 = h->E2.as<double>();
+  a.A0 = Ad; a.A1 = Ad + m;
+  a.M = h->Mbuf.p; a.ld = h->ld; a.m = (int)m; a.row0 = h->row0; a.rows = h->rows; a.rows_pad = h->rows_pad;
+  a.d = d; a.p0 = p0; a.p1 = p1; a.p2 = p2; a.p3 = p3; a.affinityeps = h->prm.affinityeps;
+  int rc = (h->storage == CLP_STORE_F64) ? launch_score<double>(h, kind, d, a) : launch_score<float>(h, kind, d, a);
+  if (rc) return rc;
+  SyncBlock host;
+  if ((rc = read_sync(h, &host))) return rc;
+  if (host.error == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
+  h->has_matrix = true;
+  h->has_A = true;
+  return CLP_OK;
+}
+
+int score_from_host(clp_handle h, int kind, const double* D1, int d, long long n1, const double* D2,
+                    long long n2, const int32_t* A, long long m, double p0, double p1, double p2, double p3) {
+  if (!h) return CLP_ERR_INVALID;
+  if (!D1 || !D2 || d <= 0 || n1 <= 0 || n2 <= 0) return fail(h, CLP_ERR_INVALID, "bad data set arguments");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  if (A == nullptr || m == 0) {  // all-to-all hypothesis (ref clipper.cpp:24, utils.h:61-71)
+    m = n1 * n2;
+    if (m > (long long)kMaxSeg * kSegMax) return fail(h, CLP_ERR_INVALID, "all-to-all hypothesis too large");
+    h->A_host.resize((size_t)2 * m);
+    clp_create_all_to_all(n1, n2, h->A_host.data());
+  } else {
+    if (m < 0) return fail(h, CLP_ERR_INVALID, "negative m");
+    h->A_host.assign(A, A + (size_t)2 * m);
+  }
+  h->A_host_valid = true;
+  CLP_CUDA(h, h->A_dev.ensure((size_t)2 * m * sizeof(int32_t)));
+  CLP_CUDA(h, h->D1dev.ensure((size_t)d * n1 * sizeof(double)));
+  CLP_CUDA(h, h->D2dev.ensure((size_t)d * n2 * sizeof(double)));
+  CLP_CUDA(h, cudaMemcpyAsync(h->A_dev.p, h->A_host.data(), (size_t)2 * m * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CLP_CUDA(h, cudaMemcpyAsync(h->D1dev.p, D1, (size_t)d * n1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CLP_CUDA(h, cudaMemcpyAsync(h->D2dev.p, D2, (size_t)d * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return score_on_device(h, kind, h->D1dev.as<double>(), d, n1, h->D2dev.as<double>(), n2,
+                         h->A_dev.as<int32_t>(), m, p0, p1, p2, p3);
+}
+
+int score_from_device(clp_handle h, int kind, const double* D1d, int d, long long n1, const double* D2d,
+                      long long n2, const int32_t* Ad, long long m, double p0, double p1, double p2, double p3) {
+  if (!h) return CLP_ERR_INVALID;
+  if (!D1d || !D2d || !Ad || d <= 0 || n1 <= 0 || n2 <= 0 || m <= 0)
+    return fail(h, CLP_ERR_INVALID, "bad device arguments (A_dev is required)");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  CLP_CUDA(h, h->A_dev.ensure((size_t)2 * m * sizeof(int32_t)));
+  CLP_CUDA(h, cudaMemcpyAsync(h->A_dev.p, Ad, (size_t)2 * m * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  h->A_host_valid = false;
+  return score_on_device(h, kind, D1d, d, n1, D2d, n2, h->A_dev.as<int32_t>(), m, p0, p1, p2, p3);
+}
+
+template <typename T>
+int launch_matvec(clp_handle h, const StageArgs& st, const double* v, double d, double* y, double* Mv, double* Cv) {
+  const Plan& p = h->plan;
+  double* partM = h->parts.as<double>();
+  double* partC = partM + (size_t)p.NSEG * h->rows_pad;
+  matvec_partials_kernel<T><<<p.G, kThreads, 0, h->stream>>>(mat_view(h), p, st, partM, partC);
+  CLP_CUDA(h, cudaGetLastError());
+  matvec_combine_kernel<<<(unsigned)((h->rows + 255) / 256), 256, 0, h->stream>>>(
+      mat_view(h), p, partM, partC, h->small.as<double>(), v, d, y, Mv, Cv);
+  CLP_CUDA(h, cudaGetLastError());
+  return CLP_OK;
+}
+
+int matvec_enqueue(clp_handle h, const double* v_dev, double d, double* y_dev, double* Mv_dev, double* Cv_dev) {
+  StageArgs st;
+  st.mode = STAGE_RAW; st.srcA = v_dev; st.srcB = nullptr; st.alpha = 0.0; st.z = 1.0; st.dst = nullptr;
+  st.segsum = h->small.as<double>();
+  return (h->storage == CLP_STORE_F64) ? launch_matvec<double>(h, st, v_dev, d, y_dev, Mv_dev, Cv_dev)
+                                       : launch_matvec<float>(h, st, v_dev, d, y_dev, Mv_dev, Cv_dev);
+}
+
+template <typename T>
+cudaError_t launch_solver(clp_handle h, SolverArgs& a) {
+  void* args[] = {&a};
+  return cudaLaunchCooperativeKernel((const void*)solver_kernel<T>, dim3(h->plan.G), dim3(kThreads), args, 0, h->stream);
+}
+
+struct ResultHeader {  // first 256 bytes of the result buffer
+  SolverOut out;
+};
+
+// u0 already in h->u0dev; runs the persistent kernel, brings back scalars + u, rounds on the host
+int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_out_dev, int32_t* nodes_out,
+               std::chrono::steady_clock::time_point t_begin) {
+  const clp_params& P = h->prm;
+  if (P.maxlsiters < 1) return fail(h, CLP_ERR_INVALID, "maxlsiters must be >= 1");
+  if (h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "sharded solve goes through clp_shard_solve");
+  SolverArgs a;
+  a.mv = mat_view(h);
+  a.plan = h->plan;
+  a.prm.tol_u = P.tol_u; a.prm.tol_F = P.tol_F; a.prm.beta = P.beta; a.prm.eps = P.eps;
+  a.prm.maxiniters = P.maxiniters; a.prm.maxoliters = P.maxoliters; a.prm.maxlsiters = P.maxlsiters;
+  a.prm.rescale_u0 = P.rescale_u0 ? 1 : 0;
+  SyncBlock* sb = h->sync.as<SyncBlock>();
+  a.bar.counter = &sb->counter; a.bar.error = &sb->error; a.bar.nblocks = (unsigned)h->plan.G;
+  a.u0 = h->u0dev.as<double>();
+  double* v = h->vecs.as<double>();
+  a.U[0] = v; a.U[1] = v + h->mpad; a.Gd[0] = v + 2 * h->mpad; a.Gd[1] = v + 3 * h->mpad;
+  a.MV[0] = v + 4 * h->mpad; a.MV[1] = v + 5 * h->mpad; a.CV[0] = v + 6 * h->mpad; a.CV[1] = v + 7 * h->mpad;
+  a.partM = h->parts.as<double>();
+  a.partC = a.partM + (size_t)h->plan.NSEG * h->rows_pad;
+  a.segsum = h->small.as<double>();
+  a.red = h->small.as<double>() + kMaxSeg;
+  a.out = reinterpret_cast<SolverOut*>(h->result.p);
+  a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
+
+  if (int rc = reset_sync(h)) return rc;
+  CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  cudaError_t le = (h->storage == CLP_STORE_F64) ? launch_solver<double>(h, a) : launch_solver<float>(h, a);
+  CLP_CUDA(h, le);
+  CLP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  const size_t rbytes = 256 + (size_t)h->m * sizeof(double);
+  CLP_CUDA(h, cudaMemcpyAsync(h->pinned, h->result.p, rbytes, cudaMemcpyDeviceToHost, h->stream));
+  if (u_out_dev)
+    CLP_CUDA(h, cudaMemcpyAsync(u_out_dev, a.u_final, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CLP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+
+  const SolverOut so = *reinterpret_cast<const SolverOut*>(h->pinned);
+  if (so.status != 0) return fail(h, CLP_ERR_TIMEOUT, "solver kernel: device-wide barrier timed out");
+  const double* u = reinterpret_cast<const double*>(reinterpret_cast<const char*>(h->pinned) + 256);
+
+  // rounding (ref clipper.cpp:287-310) on the device-produced u
+  std::vector<int32_t> nodes;
+  if (P.rounding == CLP_ROUND_NONZERO) {
+    nodes.resize((size_t)h->m);
+    nodes.resize((size_t)clp_find_above(u, h->m, 0.0, nodes.data()));
+  } else if (P.rounding == CLP_ROUND_DSD_HEU) {
+    const int omega = (int)std::round(so.F);
+    if (omega >= 1) {
+      nodes.resize((size_t)std::min<long long>(omega, h->m));
+      nodes.resize((size_t)clp_find_k_largest(u, h->m, omega, nodes.data()));
+    }
+  } else if (P.rounding == CLP_ROUND_DSD) {
+    std::vector<int32_t> S((size_t)h->m);
+    S.resize((size_t)clp_find_above(u, h->m, 0.0, S.data()));
+    const int k = (int)S.size();
+    if (k > 0) {
+      // ship only the k x k sub-block of M induced by support(u)
+      CLP_CUDA(h, h->cscbuf.ensure((size_t)k * sizeof(int32_t) + (size_t)k * k * sizeof(double) + 16));
+      double* sub_d = h->cscbuf.as<double>();
+      int32_t* S_d = reinterpret_cast<int32_t*>(sub_d + (size_t)k * k);
+      CLP_CUDA(h, cudaMemcpyAsync(S_d, S.data(), (size_t)k * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      dim3 g((unsigned)((k + 127) / 128), (unsigned)k);
+      if (h->storage == CLP_STORE_F64) gather_subblock_kernel<double><<<g, 128, 0, h->stream>>>(h->Mbuf.as<double>(), h->ld, S_d, k, sub_d);
+      else gather_subblock_kernel<float><<<g, 128, 0, h->stream>>>(h->Mbuf.as<float>(), h->ld, S_d, k, sub_d);
+      CLP_CUDA(h, cudaGetLastError());
+      std::vector<double> sub((size_t)k * k);
+      CLP_CUDA(h, cudaMemcpyAsync(sub.data(), sub_d, sub.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (k > 8192) return fail(h, CLP_ERR_UNSUPPORTED, "Rounding::DSD: support(u) larger than 8192 nodes");
+      // n_total = m: the reference runs dsd::solve on the full M_ restricted to S (clipper.cpp:299)
+      const std::vector<int32_t> sel = clp::densest_subgraph_dense(sub.data(), k, h->m);
+      nodes.resize(sel.size());
+      for (size_t i = 0; i < sel.size(); ++i) nodes[i] = S[(size_t)sel[i]];
+    }
+  } else {
+    return fail(h, CLP_ERR_INVALID, "unknown rounding mode");
+  }
+
+  if (u_out_host) std::memcpy(u_out_host, u, (size_t)h->m * sizeof(double));
+  if (nodes_out && !nodes.empty()) std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(int32_t));
+  if (out) {
+    out->ifinal = so.ifinal; out->n_nodes = (int32_t)nodes.size(); out->score = so.F; out->d_final = so.d;
+    out->n_evals = so.n_evals; out->n_matvec = so.n_matvec; out->n_inner = so.n_inner; out->kernel_ms = ms;
+    out->t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  }
+  return CLP_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C-ABI
+// ==========================================================================================
+extern "C" {
+
+const char* clp_version(void) { return "clipper_b200 " CLP_VERSION " (sm_100a, dense f32/f64 store, fp64 solver)"; }
+
+void clp_default_params(clp_params* p) {
+  if (!p) return;
+  p->tol_u = 1e-8; p->tol_F = 1e-9; p->tol_Fop = 1e-10;
+  p->maxiniters = 200; p->maxoliters = 1000;
+  p->beta = 0.25; p->maxlsiters = 99;
+  p->eps = 1e-9; p->affinityeps = 1e-4;
+  p->rescale_u0 = 1; p->rounding = CLP_ROUND_DSD_HEU;
+}
+
+int clp_create(int device, int storage, clp_handle* out) {
+  if (!out) return CLP_ERR_INVALID;
+  *out = nullptr;
+  if (storage != CLP_STORE_F32 && storage != CLP_STORE_F64) return fail(nullptr, CLP_ERR_INVALID, "unknown storage type");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, CLP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, CLP_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, CLP_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, CLP_ERR_CUDA, "clipper_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  if (!prop.cooperativeLaunch) return fail(nullptr, CLP_ERR_CUDA, "device lacks cooperative launch");
+  clp_handle h = new (std::nothrow) clp_handle_s();
+  if (!h) return fail(nullptr, CLP_ERR_ALLOC, "host allocation failed");
+  h->device = device; h->storage = storage; h->sm_count = prop.multiProcessorCount;
+  clp_default_params(&h->prm);
+  auto bail = [&](const char* what, cudaError_t ce) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    clp_destroy(h);
+    return CLP_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = h->sync.ensure(sizeof(SyncBlock))) != cudaSuccess) return bail("cudaMalloc", e);
+  int occ = 0;
+  if (storage == CLP_STORE_F64) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solver_kernel<double>, kThreads, 0);
+  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solver_kernel<float>, kThreads, 0);
+  if (e != cudaSuccess || occ < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
+  h->ctas_per_sm = std::min(occ, 2);
+  *out = h;
+  return CLP_OK;
+}
+
+int clp_destroy(clp_handle h) {
+  if (!h) return CLP_OK;
+  cudaSetDevice(h->device);
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->parts, &h->small,
+                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
+    b->release();
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CLP_OK;
+}
+
+const char* clp_last_error(clp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int clp_set_params(clp_handle h, const clp_params* p) {
+  if (!h || !p) return CLP_ERR_INVALID;
+  if (p->rounding < 0 || p->rounding > 2) return fail(h, CLP_ERR_INVALID, "unknown rounding mode");
+  h->prm = *p;
+  return CLP_OK;
+}
+int clp_get_params(clp_handle h, clp_params* p) {
+  if (!h || !p) return CLP_ERR_INVALID;
+  *p = h->prm;
+  return CLP_OK;
+}
+
+int clp_set_stream(clp_handle h, void* cuda_stream) {
+  if (!h) return CLP_ERR_INVALID;
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (cuda_stream) { h->stream = reinterpret_cast<cudaStream_t>(cuda_stream); h->own_stream = false; }
+  else { CLP_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  return CLP_OK;
+}
+
+// ---- scoring ------------------------------------------------------------------------------
+int clp_score_euclidean(clp_handle h, const double* D1, int32_t d, int64_t n1, const double* D2, int64_t n2,
+                        const int32_t* A, int64_t m, double sigma, double epsilon, double mindist) {
+  return score_from_host(h, 0, D1, d, n1, D2, n2, A, m, sigma, epsilon, mindist, 0.0);
+}
+int clp_score_pointnormal(clp_handle h, const double* D1, int64_t n1, const double* D2, int64_t n2,
+                          const int32_t* A, int64_t m, double sigp, double epsp, double sign, double epsn) {
+  return score_from_host(h, 1, D1, 6, n1, D2, n2, A, m, sigp, epsp, sign, epsn);
+}
+int clp_score_euclidean_dev(clp_handle h, const double* D1, int32_t d, int64_t n1, const double* D2, int64_t n2,
+                            const int32_t* A, int64_t m, double sigma, double epsilon, double mindist) {
+  return score_from_device(h, 0, D1, d, n1, D2, n2, A, m, sigma, epsilon, mindist, 0.0);
+}
+int clp_score_pointnormal_dev(clp_handle h, const double* D1, int64_t n1, const double* D2, int64_t n2,
+                              const int32_t* A, int64_t m, double sigp, double epsp, double sign, double epsn) {
+  return score_from_device(h, 1, D1, 6, n1, D2, n2, A, m, sigp, epsp, sign, epsn);
+}
+
+// ---- get / set ----------------------------------------------------------------------------
+int clp_set_dense(clp_handle h, const double* M, const double* C, int64_t m) {
+  if (!h || !M || !C) return CLP_ERR_INVALID;
+  if (int rc = ensure_matrix(h, m)) return rc;
+  h->has_A = false; h->A_host_valid = false;
+  if (int rc = reset_sync(h)) return rc;
+  SyncBlock* sb = h->sync.as<SyncBlock>();
+  const size_t total = (size_t)h->rows_pad * (size_t)h->ld;
+  if (h->storage == CLP_STORE_F64) fill_neutral_kernel<double><<<h->sm_count * 8, 256, 0, h->stream>>>(h->Mbuf.as<double>(), total);
+  else fill_neutral_kernel<float><<<h->sm_count * 8, 256, 0, h->stream>>>(h->Mbuf.as<float>(), total);
+  CLP_CUDA(h, cudaGetLastError());
+  // column panels of at most 32 MB per matrix
+  const long long pc = std::max<long long>(1, std::min<long long>(m, (32ll << 20) / (8 * m)));
+  CLP_CUDA(h, h->panel.ensure((size_t)2 * pc * m * sizeof(double)));
+  double* Mp = h->panel.as<double>();
+  double* Cp = Mp + (size_t)pc * m;
+  for (long long j0 = 0; j0 < m; j0 += pc) {
+    const long long j1 = std::min<long long>(m, j0 + pc);
+    CLP_CUDA(h, cudaMemcpyAsync(Mp, M + (size_t)j0 * m, (size_t)(j1 - j0) * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CLP_CUDA(h, cudaMemcpyAsync(Cp, C + (size_t)j0 * m, (size_t)(j1 - j0) * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)(j1 - j0));
+    if (h->storage == CLP_STORE_F64)
+      encode_dense_panel_kernel<double><<<grid, 256, 0, h->stream>>>(Mp, Cp, (int)m, (int)j0, (int)j1, h->Mbuf.as<double>(), h->ld, h->row0, h->rows, &sb->flags);
+    else
+      encode_dense_panel_kernel<float><<<grid, 256, 0, h->stream>>>(Mp, Cp, (int)m, (int)j0, (int)j1, h->Mbuf.as<float>(), h->ld, h->row0, h->rows, &sb->flags);
+    CLP_CUDA(h, cudaGetLastError());
+    CLP_CUDA(h, cudaStreamSynchronize(h->stream));  // the panel buffer is reused
+  }
+  SyncBlock host;
+  if (int rc = read_sync(h, &host)) return rc;
+  if (host.flags & 1) return fail(h, CLP_ERR_UNSUPPORTED, "affinity matrix has negative entries (contract: M in [0,1], ref clipper.h:166-171)");
+  if (host.flags & 2) return fail(h, CLP_ERR_UNSUPPORTED, "constraint matrix is not binary (contract: ref clipper.h:176)");
+  h->has_matrix = true;
+  return CLP_OK;
+}
+
+int clp_set_sparse_upper(clp_handle h, int64_t m, const int64_t* cpM, const int32_t* riM, const double* vM,
+                         const int64_t* cpC, const int32_t* riC, const double* vC) {
+  if (!h || !cpM || !cpC) return CLP_ERR_INVALID;
+  if (int rc = ensure_matrix(h, m)) return rc;
+  h->has_A = false; h->A_host_valid = false;
+  if (int rc = reset_sync(h)) return rc;
+  SyncBlock* sb = h->sync.as<SyncBlock>();
+  const size_t total = (size_t)h->rows_pad * (size_t)h->ld;
+  if (h->storage == CLP_STORE_F64) fill_neutral_kernel<double><<<h->sm_count * 8, 256, 0, h->stream>>>(h->Mbuf.as<double>(), total);
+  else fill_neutral_kernel<float><<<h->sm_count * 8, 256, 0, h->stream>>>(h->Mbuf.as<float>(), total);
+  CLP_CUDA(h, cudaGetLastError());
+  for (int which = 0; which < 2; ++which) {
+    const int64_t* cp = which ? cpC : cpM; const int32_t* ri = which ? riC : riM; const double* vv = which ? vC : vM;
+    const long long nnz = cp[m];
+    if (nnz < 0) return fail(h, CLP_ERR_INVALID, "bad CSC column pointer");
+    const size_t b_cp = (size_t)(m + 1) * sizeof(long long), b_v = (size_t)std::max<long long>(nnz, 1) * sizeof(double);
+    const size_t b_ri = (size_t)std::max<long long>(nnz, 1) * sizeof(int32_t);
+    CLP_CUDA(h, h->cscbuf.ensure(b_cp + b_v + b_ri + 64));
+    char* base = h->cscbuf.as<char>();
+    long long* cp_d = reinterpret_cast<long long*>(base);
+    double* v_d = reinterpret_cast<double*>(base + b_cp);
+    int32_t* ri_d = reinterpret_cast<int32_t*>(base + b_cp + b_v);
+    CLP_CUDA(h, cudaMemcpyAsync(cp_d, cp, b_cp, cudaMemcpyHostToDevice, h->stream));
+    if (nnz > 0) {
+      CLP_CUDA(h, cudaMemcpyAsync(v_d, vv, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CLP_CUDA(h, cudaMemcpyAsync(ri_d, ri, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h->storage == CLP_STORE_F64) {
+      if (which == 0) scatter_csc_M_kernel<double><<<(unsigned)m, 128, 0, h->stream>>>(cp_d, ri_d, v_d, (int)m, h->Mbuf.as<double>(), h->ld, h->row0, h->rows, &sb->flags);
+      else scatter_csc_C_kernel<double><<<(unsigned)m, 128, 0, h->stream>>>(cp_d, ri_d, v_d, (int)m, h->Mbuf.as<double>(), h->ld, h->row0, h->rows, &sb->flags);
+    } else {
+      if (which == 0) scatter_csc_M_kernel<float><<<(unsigned)m, 128, 0, h->stream>>>(cp_d, ri_d, v_d, (int)m, h->Mbuf.as<float>(), h->ld, h->row0, h->rows, &sb->flags);
+      else scatter_csc_C_kernel<float><<<(unsigned)m, 128, 0, h->stream>>>(cp_d, ri_d, v_d, (int)m, h->Mbuf.as<float>(), h->ld, h->row0, h->rows, &sb->flags);
+    }
+    CLP_CUDA(h, cudaGetLastError());
+    CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  SyncBlock host;
+  if (int rc = read_sync(h, &host)) return rc;
+  if (host.flags & 4) return fail(h, CLP_ERR_INVALID, "sparse input is not strictly upper triangular (ref clipper.h:137-138)");
+  if (host.flags & 1) return fail(h, CLP_ERR_UNSUPPORTED, "affinity matrix has negative entries");
+  if (host.flags & 2) return fail(h, CLP_ERR_UNSUPPORTED, "constraint matrix is not binary");
+  h->has_matrix = true;
+  return CLP_OK;
+}
+
+int clp_get_dense(clp_handle h, int which, double* out) {
+  if (!h || !out) return CLP_ERR_INVALID;
+  if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "no affinity matrix has been scored or set");
+  if (h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "clp_get_dense on a sharded handle");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  const long long m = h->m;
+  const long long pc = std::max<long long>(1, std::min<long long>(m, (64ll << 20) / (8 * m)));
+  CLP_CUDA(h, h->panel.ensure((size_t)pc * m * sizeof(double)));
+  double* P = h->panel.as<double>();
+  for (long long j0 = 0; j0 < m; j0 += pc) {
+    const long long j1 = std::min<long long>(m, j0 + pc);
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)(j1 - j0));
+    if (h->storage == CLP_STORE_F64) decode_dense_panel_kernel<double><<<grid, 256, 0, h->stream>>>(h->Mbuf.as<double>(), h->ld, (int)m, (int)j0, (int)j1, which, P);
+    else decode_dense_panel_kernel<float><<<grid, 256, 0, h->stream>>>(h->Mbuf.as<float>(), h->ld, (int)m, (int)j0, (int)j1, which, P);
+    CLP_CUDA(h, cudaGetLastError());
+    CLP_CUDA(h, cudaMemcpyAsync(out + (size_t)j0 * m, P, (size_t)(j1 - j0) * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return CLP_OK;
+}
+
+int clp_num_associations(clp_handle h, int64_t* m) {
+  if (!h || !m) return CLP_ERR_INVALID;
+  *m = h->has_matrix ? h->m : 0;
+  return CLP_OK;
+}
+
+int clp_get_associations(clp_handle h, int32_t* A) {
+  if (!h || !A) return CLP_ERR_INVALID;
+  if (!h->has_A) return fail(h, CLP_ERR_INVALID, "no associations: the matrix was not built by scorePairwiseConsistency");
+  if (!h->A_host_valid) {
+    h->A_host.resize((size_t)2 * h->m);
+    CLP_CUDA(h, cudaSetDevice(h->device));
+    CLP_CUDA(h, cudaMemcpyAsync(h->A_host.data(), h->A_dev.p, (size_t)2 * h->m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->A_host_valid = true;
+  }
+  std::memcpy(A, h->A_host.data(), (size_t)2 * h->m * sizeof(int32_t));
+  return CLP_OK;
+}
+
+int clp_count_nonzeros(clp_handle h, int64_t* nnzM, int64_t* nnzC) {
+  if (!h) return CLP_ERR_INVALID;
+  if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "no affinity matrix");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  if (int rc = reset_sync(h)) return rc;
+  SyncBlock* sb = h->sync.as<SyncBlock>();
+  if (h->storage == CLP_STORE_F64) count_upper_kernel<double><<<h->sm_count * 8, 256, 0, h->stream>>>(h->Mbuf.as<double>(), h->ld, (int)h->m, h->row0, h->rows, sb->counts);
+  else count_upper_kernel<float><<<h->sm_count * 8, 256, 0, h->stream>>>(h->Mbuf.as<float>(), h->ld, (int)h->m, h->row0, h->rows, sb->counts);
+  CLP_CUDA(h, cudaGetLastError());
+  SyncBlock host;
+  if (int rc = read_sync(h, &host)) return rc;
+  if (nnzM) *nnzM = (int64_t)host.counts[0];
+  if (nnzC) *nnzC = (int64_t)host.counts[1];
+  return CLP_OK;
+}
+
+// ---- solve --------------------------------------------------------------------------------
+int clp_solve(clp_handle h, const double* u0, clp_solution* out, double* u_out, int32_t* nodes_out, double* u0_out) {
+  if (!h) return CLP_ERR_INVALID;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "solve() before any affinity matrix was scored or set");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  double* stage = reinterpret_cast<double*>(reinterpret_cast<char*>(h->pinned) + 256);
+  if (u0) {
+    std::memcpy(stage, u0, (size_t)h->m * sizeof(double));
+  } else {  // utils::randvec (ref utils.cpp:22-29): U[0,1) seeded from std::random_device
+    std::random_device rd;
+    std::mt19937 gen(rd());
+    std::uniform_real_distribution<double> dis(0, 1);
+    for (long long i = 0; i < h->m; ++i) stage[i] = dis(gen);
+  }
+  if (u0_out) std::memcpy(u0_out, stage, (size_t)h->m * sizeof(double));
+  CLP_CUDA(h, cudaMemcpyAsync(h->u0dev.p, stage, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return solve_core(h, out, u_out, nullptr, nodes_out, t0);
+}
+
+int clp_solve_dev(clp_handle h, const double* u0_dev, clp_solution* out, double* u_out_dev, int32_t* nodes_out) {
+  if (!h || !u0_dev) return CLP_ERR_INVALID;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "solve() before any affinity matrix was scored or set");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  CLP_CUDA(h, cudaMemcpyAsync(h->u0dev.p, u0_dev, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return solve_core(h, out, nullptr, u_out_dev, nodes_out, t0);
+}
+
+// ---- mat-vec ------------------------------------------------------------------------------
+int clp_matvec(clp_handle h, const double* v, double d, double* y, double* Mv, double* Cv) {
+  if (!h || !v) return CLP_ERR_INVALID;
+  if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "no affinity matrix");
+  if (h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "clp_matvec on a sharded handle");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  double* b = h->ybuf.as<double>();
+  const size_t vb = (size_t)h->m * sizeof(double);
+  CLP_CUDA(h, cudaMemcpyAsync(b, v, vb, cudaMemcpyHostToDevice, h->stream));
+  if (int rc = matvec_enqueue(h, b, d, b + h->mpad, b + 2 * h->mpad, b + 3 * h->mpad)) return rc;
+  if (y) CLP_CUDA(h, cudaMemcpyAsync(y, b + h->mpad, vb, cudaMemcpyDeviceToHost, h->stream));
+  if (Mv) CLP_CUDA(h, cudaMemcpyAsync(Mv, b + 2 * h->mpad, vb, cudaMemcpyDeviceToHost, h->stream));
+  if (Cv) CLP_CUDA(h, cudaMemcpyAsync(Cv, b + 3 * h->mpad, vb, cudaMemcpyDeviceToHost, h->stream));
+  CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLP_OK;
+}
+
+int clp_matvec_dev(clp_handle h, const double* v_dev, double d, double* y_dev, double* Mv_dev, double* Cv_dev,
+                   int reps, double* ms_per_launch) {
+  if (!h || !v_dev || reps < 1) return CLP_ERR_INVALID;
+  if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "no affinity matrix");
+  if (h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "clp_matvec_dev on a sharded handle");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; ++r)
+    if (int rc = matvec_enqueue(h, v_dev, d, y_dev, Mv_dev, Cv_dev)) return rc;
+  CLP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CLP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (ms_per_launch) *ms_per_launch = (double)ms / reps;
+  return CLP_OK;
+}
+
+// ---- multi-GPU (row-block sharding) --------------------------------------------------------
+int clp_shard_config(clp_handle h, int rank, int world) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return CLP_ERR_INVALID;
+  h->rank = rank; h->world = world; h->has_matrix = false;
+  return CLP_OK;
+}
+int64_t clp_shard_blob_bytes(void) { return 256; }
+int clp_shard_export(clp_handle h, void*, int64_t, int64_t*) { return fail(h, CLP_ERR_UNSUPPORTED, "peer-memory solver not built yet"); }
+int clp_shard_import(clp_handle h, const void*, int64_t, int) { return fail(h, CLP_ERR_UNSUPPORTED, "peer-memory solver not built yet"); }
+int clp_shard_solve(clp_handle h, const double*, clp_solution*, double*, int32_t*) { return fail(h, CLP_ERR_UNSUPPORTED, "peer-memory solver not built yet"); }
+
+}  // extern "C"

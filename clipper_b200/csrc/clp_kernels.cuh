@@ -1,0 +1,879 @@
+// clp_kernels.cuh -- sm_100a device code of the CLIPPER hot path.
+//
+//   K1  score_tile_kernel     scorePairwiseConsistency + invariants   (ref clipper.cpp:21-65,
+//                             euclidean_distance.cpp:13-31, pointnormal_distance.cpp:13-35)
+//   K2  matvec_*              penalised mat-vec  Mhat v, Chat v       (ref clipper.cpp:194-271)
+//   K3-K5 solver_kernel       whole findDenseClique() as ONE persistent cooperative kernel:
+//                             step/projection, objective, backtracking line search, penalty
+//                             ramp, all decided on the device            (ref clipper.cpp:172-283)
+//   K7  encode/decode kernels  get/setMatrixData                        (ref clipper.cpp:131-166)
+//
+// Data layout in HBM.  The affinity matrix is DENSE and symmetric, row-major with a leading
+// dimension ld (multiple of 128 elements) and the row count padded to a multiple of 32.  One
+// stored element s carries BOTH matrices of the reference:
+//        M_ij = |s|            C_ij = (sign bit of s clear)
+// so "inconsistent" (M=0,C=0) is -0.0, "consistent" is +score, "no affinity but no penalty"
+// (M=0,C=1, legal through setMatrixData) is +0.0.  The diagonal is stored as -0.0 and the
+// identity is applied analytically exactly like the reference does (clipper.cpp:58,194,238).
+// Storage type T is float (default; 4 B/entry is the only O(m^2) traffic) or double.
+// Every O(m) vector, every accumulator and every scalar decision is fp64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace clp {
+
+constexpr int kThreads = 256;          // threads per CTA everywhere
+constexpr int kWarps = kThreads / 32;  // 8
+constexpr int kRowsPerWarp = 4;        // register blocking of the mat-vec (rows per warp)
+constexpr int kRowTile = kWarps * kRowsPerWarp;  // 32 rows per CTA item
+constexpr int kSegMax = 4096;          // max columns of v staged in shared memory per pass
+constexpr int kMaxSeg = 64;            // max number of column segments (m <= 262144)
+constexpr int kRedVals = 8;            // doubles per CTA in the partial-reduction table
+
+enum StageMode : int { STAGE_RAW = 0, STAGE_DIV = 1, STAGE_STEP = 2 };
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// element -> (|s| as double, C bit)
+__device__ __forceinline__ void decode(float s, double& a, bool& c) {
+  a = (double)fabsf(s);
+  c = __float_as_int(s) >= 0;
+}
+__device__ __forceinline__ void decode(double s, double& a, bool& c) {
+  a = fabs(s);
+  c = __double2hiint(s) >= 0;
+}
+template <typename T> __device__ __forceinline__ T encode(double mval, bool cbit);
+template <> __device__ __forceinline__ float encode<float>(double mval, bool cbit) {
+  const float a = fabsf((float)mval);
+  return cbit ? a : -a;
+}
+template <> __device__ __forceinline__ double encode<double>(double mval, bool cbit) {
+  const double a = fabs(mval);
+  return cbit ? a : -a;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-wide barrier for the persistent kernels (all CTAs co-resident: cooperative launch).
+// Monotonic ticket counter, no reset; bounded spin so a lost CTA can never hang the GPU.
+// ------------------------------------------------------------------------------------------
+struct GridBar {
+  unsigned long long* counter;  // device global, zero-initialised
+  int* error;                   // device global, set to 1 on timeout
+  unsigned int nblocks;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(const GridBar& b) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(b.counter, 1ULL);
+    const unsigned long long target = (old / b.nblocks + 1ULL) * b.nblocks;
+    const long long t0 = clock64();
+    while (ld_acquire_u64(b.counter) < target) {
+      __nanosleep(32);
+      if (clock64() - t0 > 4000000000LL) {  // ~2 s: give up, flag, fall through
+        atomicExch(b.error, 1);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: scoring
+// ------------------------------------------------------------------------------------------
+struct ScoreArgs {
+  const double* E1;  // [m][d] endpoint in data set 1 of association i  (D1.col(A(i,0)))
+  const double* E2;  // [m][d] endpoint in data set 2                   (D2.col(A(i,1)))
+  const int* A0;     // A(:,0)
+  const int* A1;     // A(:,1)
+  void* M;           // T [rows_pad][ld]
+  long long ld;
+  int m;
+  int row0;          // first global row stored here (row-block sharding)
+  int rows;          // number of real local rows
+  int rows_pad;
+  int d;             // runtime dimension (generic path)
+  double p0, p1, p2, p3;  // sigma,epsilon,mindist | sigp,epsp,sign,epsn
+  double affinityeps;
+};
+
+template <int D>
+__device__ __forceinline__ double point_dist(const double* a, const double* b, int d_rt) {
+  double s = 0.0;
+  if (D > 0) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) { const double t = __dsub_rn(a[q], b[q]); s = __dadd_rn(s, __dmul_rn(t, t)); }
+  } else {
+    for (int q = 0; q < d_rt; ++q) { const double t = __dsub_rn(a[q], b[q]); s = __dadd_rn(s, __dmul_rn(t, t)); }
+  }
+  return __dsqrt_rn(s);
+}
+
+// EuclideanDistance::operator()  (ref euclidean_distance.cpp:13-31), same operation order as
+// the oracle, no FMA contraction in the distance / exponent argument.
+__device__ __forceinline__ double euclid_score(double l1, double l2, double sigma, double epsilon,
+                                               double mindist) {
+  if (mindist > 0 && (l1 < mindist || l2 < mindist)) return 0.0;
+  const double c = fabs(__dsub_rn(l1, l2));
+  if (!(c < epsilon)) return 0.0;
+  const double arg = __ddiv_rn(__dmul_rn(__dmul_rn(-0.5, c), c), __dmul_rn(sigma, sigma));
+  return exp(arg);
+}
+
+// PointNormalDistance::operator()  (ref pointnormal_distance.cpp:13-35). acos is NOT clamped:
+// |dot|>1 gives NaN, both comparisons are false, the score is 0.
+__device__ __forceinline__ double pointnormal_score(double l1, double l2, double dot1, double dot2,
+                                                    double sigp, double epsp, double sign, double epsn) {
+  const double alpha1 = acos(dot1);
+  const double alpha2 = acos(dot2);
+  const double dp = fabs(__dsub_rn(l1, l2));
+  const double dn = fabs(__dsub_rn(alpha1, alpha2));
+  if (dp < epsp && dn < epsn) {
+    const double sp = exp(__ddiv_rn(__dmul_rn(__dmul_rn(-0.5, dp), dp), __dmul_rn(sigp, sigp)));
+    const double sn = exp(__ddiv_rn(__dmul_rn(__dmul_rn(-0.5, dn), dn), __dmul_rn(sign, sign)));
+    return __dmul_rn(sp, sn);
+  }
+  return 0.0;
+}
+
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Quad<double> {
+  static __device__ __forceinline__ void store(double* p, const double* v) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+  }
+};
+
+// One CTA = a 32-row x 128-column tile of the padded dense matrix; warp w owns 4 rows, lane l
+// owns 4 consecutive columns -> every row is written as 512 B (float) of consecutive float4.
+// KIND 0: EuclideanDistance with compile-time dimension D (D==0: runtime d). KIND 1: PointNormal.
+template <typename T, int KIND, int D>
+__global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
+  constexpr int DD = (KIND == 1) ? 6 : D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 128 + lane * 4;
+  const int lr0 = blockIdx.y * kRowTile + warp * kRowsPerWarp;  // local row
+  T* Mbase = reinterpret_cast<T*>(a.M);
+  const int dd = (DD > 0) ? DD : a.d;
+
+  T out[kRowsPerWarp][4];
+#pragma unroll
+  for (int q = 0; q < kRowsPerWarp; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[q][e] = encode<T>(0.0, false);
+
+  // row endpoints are warp-uniform: fetched through the read-only path as broadcasts
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = c0 + e;
+    if (j >= a.m) continue;
+    const int aj0 = __ldg(a.A0 + j), aj1 = __ldg(a.A1 + j);
+    double e1j[DD > 0 ? DD : 1], e2j[DD > 0 ? DD : 1];
+    if (DD > 0) {
+#pragma unroll
+      for (int q = 0; q < DD; ++q) { e1j[q] = __ldg(a.E1 + (size_t)j * DD + q); e2j[q] = __ldg(a.E2 + (size_t)j * DD + q); }
+    }
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+      const int li = lr0 + q;
+      const int i = a.row0 + li;
+      if (li >= a.rows || i == j) continue;
+      const int ai0 = __ldg(a.A0 + i), ai1 = __ldg(a.A1 + i);
+      if (ai0 == aj0 || ai1 == aj1) continue;  // distinctness (ref clipper.cpp:35-38)
+      double scr;
+      if (DD > 0) {
+        double e1i[DD > 0 ? DD : 1], e2i[DD > 0 ? DD : 1];
+#pragma unroll
+        for (int t = 0; t < DD; ++t) { e1i[t] = __ldg(a.E1 + (size_t)i * DD + t); e2i[t] = __ldg(a.E2 + (size_t)i * DD + t); }
+        if (KIND == 0) {
+          const double l1 = point_dist<DD>(e1i, e1j, 0), l2 = point_dist<DD>(e2i, e2j, 0);
+          scr = euclid_score(l1, l2, a.p0, a.p1, a.p2);
+        } else {
+          const double l1 = point_dist<3>(e1i, e1j, 0), l2 = point_dist<3>(e2i, e2j, 0);
+          const double dot1 = __dadd_rn(__dadd_rn(__dmul_rn(e1i[3], e1j[3]), __dmul_rn(e1i[4], e1j[4])), __dmul_rn(e1i[5], e1j[5]));
+          const double dot2 = __dadd_rn(__dadd_rn(__dmul_rn(e2i[3], e2j[3]), __dmul_rn(e2i[4], e2j[4])), __dmul_rn(e2i[5], e2j[5]));
+          scr = pointnormal_score(l1, l2, dot1, dot2, a.p0, a.p1, a.p2, a.p3);
+        }
+      } else {
+        const double l1 = point_dist<0>(a.E1 + (size_t)i * dd, a.E1 + (size_t)j * dd, dd);
+        const double l2 = point_dist<0>(a.E2 + (size_t)i * dd, a.E2 + (size_t)j * dd, dd);
+        scr = euclid_score(l1, l2, a.p0, a.p1, a.p2);
+      }
+      if (scr > a.affinityeps) out[q][e] = encode<T>(scr, true);  // ref clipper.cpp:53-55
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kRowsPerWarp; ++q) {
+    const int li = lr0 + q;
+    if (li < a.rows_pad && c0 < a.ld) Quad<T>::store(Mbase + (size_t)li * a.ld + c0, out[q]);
+  }
+}
+
+// E1[i][:] = D1[:, A(i,0)], E2[i][:] = D2[:, A(i,1)]; flags out-of-range association indices
+__global__ void gather_endpoints_kernel(const double* D1, const double* D2, const int* A0, const int* A1,
+                                        int m, int d, long long n1, long long n2, double* E1, double* E2,
+                                        int* error) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int a0 = A0[i], a1 = A1[i];
+  if (a0 < 0 || a0 >= n1 || a1 < 0 || a1 >= n2) { atomicExch(error, 2); return; }
+  for (int q = 0; q < d; ++q) {
+    E1[(size_t)i * d + q] = D1[(size_t)a0 * d + q];
+    E2[(size_t)i * d + q] = D2[(size_t)a1 * d + q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: the penalised mat-vec (device functions shared by the stand-alone and persistent kernels)
+// ------------------------------------------------------------------------------------------
+struct MatView {
+  const void* M;   // T [rows_pad][ld], local row block
+  long long ld;
+  int m;           // number of columns == global problem size
+  int row0;        // first global row stored locally
+  int rows;        // real local rows
+  int rows_pad;
+};
+
+struct Plan {
+  int G;     // CTAs in the grid
+  int SG;    // column-segment groups (CTA b works on segments b%SG, b%SG+SG, ...)
+  int RG;    // row groups = G / SG (CTA b works on row tiles b/SG, b/SG+RG, ...)
+  int NSEG;  // number of column segments
+  int W;     // segment width (multiple of 128, <= kSegMax)
+  int NRT;   // number of local row tiles (rows_pad / kRowTile)
+};
+
+// shared-memory position of column offset c (within a segment).  For 4-byte storage a lane owns
+// 4 consecutive columns; the two 16-byte halves of its 4 doubles are stored 64 doubles apart so
+// that both LDS.128 of a warp are bank-conflict free.
+template <typename T> __device__ __forceinline__ int vs_pos(int c);
+template <> __device__ __forceinline__ int vs_pos<float>(int c) {
+  const int q = c >> 7, r = c & 127, l = r >> 2, e = r & 3;
+  return (q << 7) + ((e >> 1) << 6) + (l << 1) + (e & 1);
+}
+template <> __device__ __forceinline__ int vs_pos<double>(int c) { return c; }
+
+struct StageArgs {
+  int mode;            // StageMode
+  const double* srcA;  // RAW/DIV: the vector; STEP: u
+  const double* srcB;  // STEP: gradF
+  double alpha;        // STEP
+  double z;            // DIV/STEP: squared norm of the un-normalised vector
+  double* dst;         // where the segment owner writes the staged (normalised) vector, or null
+  double* segsum;      // [NSEG] sum of the staged vector over each segment (written by owner)
+};
+
+// v_j for one column, exactly the reference's statement order:
+//   STEP: unew = (u + alpha*gradF).cwiseMax(0); unew.normalize()   (clipper.cpp:235-237)
+//   DIV : u /= u.norm()                                            (clipper.cpp:198)
+__device__ __forceinline__ double staged_value(const StageArgs& s, int j, double nrm) {
+  if (s.mode == STAGE_RAW) return s.srcA[j];
+  if (s.mode == STAGE_DIV) return s.srcA[j] / nrm;
+  double w = __dadd_rn(s.srcA[j], __dmul_rn(s.alpha, s.srcB[j]));
+  w = (w < 0.0) ? 0.0 : w;
+  return (s.z > 0.0) ? w / nrm : w;
+}
+
+// Stage columns [seg*W, seg*W+W) of v into shared memory (zero beyond m).  If `owner`, also
+// publish the vector and its segment sum.  All threads of the CTA must call.
+template <typename T>
+__device__ void stage_segment(const StageArgs& s, const Plan& p, int m, int seg, bool owner,
+                              double* vs, double* red_smem) {
+  const double nrm = sqrt(s.z);
+  const int cbeg = seg * p.W;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < p.W; c += kThreads) {
+    const int j = cbeg + c;
+    double v = 0.0;
+    if (j < m) {
+      v = staged_value(s, j, nrm);
+      if (owner && s.dst) s.dst[j] = v;
+    }
+    vs[vs_pos<T>(c)] = v;
+    part += v;
+  }
+  if (owner) {  // deterministic block sum: warp butterflies, then warp 0 adds the 8 partials in order
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red_smem[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kWarps; ++w) t += red_smem[w];
+      s.segsum[seg] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// One warp: rows [lr, lr+4) x the staged segment.  accM += |s| v, accC += (C bit) v.
+template <typename T> struct RowSweep;
+
+template <> struct RowSweep<float> {
+  static __device__ __forceinline__ void run(const MatView& mv, int lr, int cbeg, int W, const double* vs,
+                                             double (&accM)[kRowsPerWarp], double (&accC)[kRowsPerWarp]) {
+    const int lane = threadIdx.x & 31;
+    const float* base = reinterpret_cast<const float*>(mv.M) + (size_t)lr * mv.ld + cbeg + lane * 4;
+    const int nsteps = W >> 7;
+    int s = 0;
+    for (; s + 2 <= nsteps; s += 2) {
+      float4 a0[kRowsPerWarp], a1[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        a0[r] = ldg_stream(reinterpret_cast<const float4*>(base + (size_t)r * mv.ld + (s << 7)));
+        a1[r] = ldg_stream(reinterpret_cast<const float4*>(base + (size_t)r * mv.ld + ((s + 1) << 7)));
+      }
+      const double2 v00 = *reinterpret_cast<const double2*>(vs + (s << 7) + lane * 2);
+      const double2 v01 = *reinterpret_cast<const double2*>(vs + (s << 7) + 64 + lane * 2);
+      const double2 v10 = *reinterpret_cast<const double2*>(vs + ((s + 1) << 7) + lane * 2);
+      const double2 v11 = *reinterpret_cast<const double2*>(vs + ((s + 1) << 7) + 64 + lane * 2);
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        acc(a0[r].x, v00.x, accM[r], accC[r]); acc(a0[r].y, v00.y, accM[r], accC[r]);
+        acc(a0[r].z, v01.x, accM[r], accC[r]); acc(a0[r].w, v01.y, accM[r], accC[r]);
+        acc(a1[r].x, v10.x, accM[r], accC[r]); acc(a1[r].y, v10.y, accM[r], accC[r]);
+        acc(a1[r].z, v11.x, accM[r], accC[r]); acc(a1[r].w, v11.y, accM[r], accC[r]);
+      }
+    }
+    for (; s < nsteps; ++s) {
+      float4 a0[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r)
+        a0[r] = ldg_stream(reinterpret_cast<const float4*>(base + (size_t)r * mv.ld + (s << 7)));
+      const double2 v00 = *reinterpret_cast<const double2*>(vs + (s << 7) + lane * 2);
+      const double2 v01 = *reinterpret_cast<const double2*>(vs + (s << 7) + 64 + lane * 2);
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        acc(a0[r].x, v00.x, accM[r], accC[r]); acc(a0[r].y, v00.y, accM[r], accC[r]);
+        acc(a0[r].z, v01.x, accM[r], accC[r]); acc(a0[r].w, v01.y, accM[r], accC[r]);
+      }
+    }
+  }
+  static __device__ __forceinline__ void acc(float x, double v, double& aM, double& aC) {
+    aM = fma((double)fabsf(x), v, aM);
+    if (__float_as_int(x) >= 0) aC += v;
+  }
+};
+
+template <> struct RowSweep<double> {
+  static __device__ __forceinline__ void run(const MatView& mv, int lr, int cbeg, int W, const double* vs,
+                                             double (&accM)[kRowsPerWarp], double (&accC)[kRowsPerWarp]) {
+    const int lane = threadIdx.x & 31;
+    const double* base = reinterpret_cast<const double*>(mv.M) + (size_t)lr * mv.ld + cbeg + lane * 2;
+    const int nsteps = W >> 6;
+    int s = 0;
+    for (; s + 2 <= nsteps; s += 2) {
+      double2 a0[kRowsPerWarp], a1[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        a0[r] = ldg_stream(reinterpret_cast<const double2*>(base + (size_t)r * mv.ld + (s << 6)));
+        a1[r] = ldg_stream(reinterpret_cast<const double2*>(base + (size_t)r * mv.ld + ((s + 1) << 6)));
+      }
+      const double2 v0 = *reinterpret_cast<const double2*>(vs + (s << 6) + lane * 2);
+      const double2 v1 = *reinterpret_cast<const double2*>(vs + ((s + 1) << 6) + lane * 2);
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        acc(a0[r].x, v0.x, accM[r], accC[r]); acc(a0[r].y, v0.y, accM[r], accC[r]);
+        acc(a1[r].x, v1.x, accM[r], accC[r]); acc(a1[r].y, v1.y, accM[r], accC[r]);
+      }
+    }
+    for (; s < nsteps; ++s) {
+      double2 a0[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r)
+        a0[r] = ldg_stream(reinterpret_cast<const double2*>(base + (size_t)r * mv.ld + (s << 6)));
+      const double2 v0 = *reinterpret_cast<const double2*>(vs + (s << 6) + lane * 2);
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        acc(a0[r].x, v0.x, accM[r], accC[r]); acc(a0[r].y, v0.y, accM[r], accC[r]);
+      }
+    }
+  }
+  static __device__ __forceinline__ void acc(double x, double v, double& aM, double& aC) {
+    aM = fma(fabs(x), v, aM);
+    if (__double2hiint(x) >= 0) aC += v;
+  }
+};
+
+// Whole mat-vec phase of one CTA: for each of its segments stage v, then sweep its row tiles and
+// write the per-segment partial products  partM[seg][lrow], partC[seg][lrow].
+template <typename T>
+__device__ void matvec_phase(const MatView& mv, const Plan& p, const StageArgs& st, double* partM,
+                             double* partC, double* vs, double* red_smem) {
+  const int sg = blockIdx.x % p.SG, rg = blockIdx.x / p.SG;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int seg = sg; seg < p.NSEG; seg += p.SG) {
+    stage_segment<T>(st, p, mv.m, seg, rg == 0, vs, red_smem);
+    for (int rt = rg; rt < p.NRT; rt += p.RG) {
+      const int lr = rt * kRowTile + warp * kRowsPerWarp;
+      double accM[kRowsPerWarp], accC[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) { accM[r] = 0.0; accC[r] = 0.0; }
+      RowSweep<T>::run(mv, lr, seg * p.W, p.W, vs, accM, accC);
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) { accM[r] = warp_sum(accM[r]); accC[r] = warp_sum(accC[r]); }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+          partM[(size_t)seg * mv.rows_pad + lr + r] = accM[r];
+          partC[(size_t)seg * mv.rows_pad + lr + r] = accC[r];
+        }
+      }
+    }
+    __syncthreads();  // vs is re-staged by the next segment pass
+  }
+}
+
+// sum of the per-segment partials of local row lr, fixed order
+__device__ __forceinline__ void gather_partials(const double* partM, const double* partC, int nseg,
+                                                int rows_pad, int lr, double& Mv, double& Cv) {
+  double a = 0.0, c = 0.0;
+  for (int s = 0; s < nseg; ++s) {
+    a += partM[(size_t)s * rows_pad + lr];
+    c += partC[(size_t)s * rows_pad + lr];
+  }
+  Mv = a; Cv = c;
+}
+
+// gradF_i exactly as the reference builds it (clipper.cpp:219 / :238-241):
+//   (1 + d) * u - d * ones * u.sum() + Mhat*u + Chat*u * d      evaluated left to right
+__device__ __forceinline__ double grad_entry(double ui, double sumu, double Mv, double Cv, double d) {
+  const double t1 = __dmul_rn(__dadd_rn(1.0, d), ui);
+  const double t2 = __dmul_rn(__dmul_rn(d, 1.0), sumu);
+  return __dadd_rn(__dadd_rn(__dsub_rn(t1, t2), Mv), __dmul_rn(Cv, d));
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone mat-vec kernels (clp_matvec / the c5 sweep): partials, then combine
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+matvec_partials_kernel(MatView mv, Plan p, StageArgs st, double* partM, double* partC) {
+  __shared__ __align__(16) double vs[kSegMax];
+  __shared__ double red_smem[kWarps];
+  matvec_phase<T>(mv, p, st, partM, partC, vs, red_smem);
+}
+
+__global__ void matvec_combine_kernel(MatView mv, Plan p, const double* partM, const double* partC,
+                                      const double* segsum, const double* v, double d, double* y,
+                                      double* Mv_out, double* Cv_out) {
+  const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lr >= mv.rows) return;
+  double sumv = 0.0;
+  for (int s = 0; s < p.NSEG; ++s) sumv += segsum[s];
+  double Mv, Cv;
+  gather_partials(partM, partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
+  const int i = mv.row0 + lr;
+  if (Mv_out) Mv_out[i] = Mv;
+  if (Cv_out) Cv_out[i] = Cv;
+  if (y) y[i] = grad_entry(v[i], sumv, Mv, Cv, d);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3-K5: the persistent solver
+// ------------------------------------------------------------------------------------------
+struct SolverParams {  // clipper::Params, ref clipper.h:27-60
+  double tol_u, tol_F, beta, eps;
+  int maxiniters, maxoliters, maxlsiters, rescale_u0;
+};
+
+struct SolverOut {  // written by CTA 0 at the end
+  double F, d;
+  int ifinal, cur, status;
+  long long n_evals, n_inner, n_matvec;
+};
+
+struct SolverArgs {
+  MatView mv;
+  Plan plan;
+  SolverParams prm;
+  GridBar bar;
+  const double* u0;  // [m]
+  double* U[2];      // [mpad] current / candidate u
+  double* Gd[2];     // gradF
+  double* MV[2];     // Mhat u
+  double* CV[2];     // Chat u
+  double* partM;     // [NSEG][rows_pad]
+  double* partC;
+  double* segsum;    // [NSEG]
+  double* red;       // [2][G][kRedVals]  (double-buffered: publish/reduce alternate tables)
+  double* u_final;   // [m] copy of the final iterate (local rows)
+  SolverOut* out;
+};
+
+// every CTA reduces the per-CTA partial table in the same fixed order -> identical scalars
+__device__ void reduce_table(const double* red, int G, double (&vals)[kRedVals], double* smem /*[kWarps*kRedVals]*/) {
+  double loc[kRedVals];
+#pragma unroll
+  for (int q = 0; q < kRedVals; ++q) loc[q] = 0.0;
+  for (int b = threadIdx.x; b < G; b += kThreads) {
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) loc[q] += __ldcg(red + (size_t)b * kRedVals + q);
+  }
+#pragma unroll
+  for (int q = 0; q < kRedVals; ++q) loc[q] = warp_sum(loc[q]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) smem[warp * kRedVals + q] = loc[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kRedVals; ++q) {
+    double t = 0.0;
+    for (int w = 0; w < kWarps; ++w) t += smem[w * kRedVals + q];
+    vals[q] = t;
+  }
+  __syncthreads();
+}
+
+// CTA-level deterministic sum of per-thread partials into red[blockIdx.x][*]
+__device__ void publish_partials(const double (&loc)[kRedVals], double* red, double* smem) {
+  double t[kRedVals];
+#pragma unroll
+  for (int q = 0; q < kRedVals; ++q) t[q] = warp_sum(loc[q]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) smem[warp * kRedVals + q] = t[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < kRedVals) {
+    double s = 0.0;
+    for (int w = 0; w < kWarps; ++w) s += smem[w * kRedVals + threadIdx.x];
+    red[(size_t)blockIdx.x * kRedVals + threadIdx.x] = s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
+  __shared__ __align__(16) double vs[kSegMax];
+  __shared__ double red_smem[kWarps * kRedVals];
+  const MatView& mv = a.mv;
+  const Plan& p = a.plan;
+  const SolverParams& P = a.prm;
+  const int gtid = blockIdx.x * kThreads + threadIdx.x;
+  const int gthreads = p.G * kThreads;
+  double vals[kRedVals];
+  double loc[kRedVals];
+
+  long long n_evals = 0, n_inner = 0, n_matvec = 0;
+  int cur = 0;  // U[cur], Gd[cur], MV[cur], CV[cur] describe the current iterate
+  double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0;
+  int i_outer = 0;
+  int status = 0;
+
+  // The partial-sum table is double-buffered: a CTA may publish round r+1 while a slower CTA
+  // still reduces round r (there is no barrier between a reduce and the next publish).
+  int red_par = 0;
+#define CLP_ZERO_LOC()            \
+  _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
+#define CLP_PUBLISH()                                                                   \
+  publish_partials(loc, a.red + (size_t)red_par * p.G * kRedVals, red_smem);
+#define CLP_REDUCE()                                                                    \
+  reduce_table(a.red + (size_t)red_par * p.G * kRedVals, p.G, vals, red_smem);          \
+  red_par ^= 1;
+#define CLP_BAR_CHECK()                                               \
+  grid_barrier(a.bar);                                                \
+  if (*reinterpret_cast<volatile int*>(a.bar.error) != 0) { status = 5; goto finish; }
+
+  // ---- initialisation: one power step (clipper.cpp:193-198) ------------------------------
+  {
+    StageArgs st;
+    st.srcB = nullptr; st.alpha = 0.0; st.segsum = a.segsum;
+    if (P.rescale_u0) {
+      st.mode = STAGE_RAW; st.srcA = a.u0; st.z = 1.0; st.dst = nullptr;
+      matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec;
+      CLP_BAR_CHECK();
+    }
+    CLP_ZERO_LOC();
+    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+      const int i = mv.row0 + lr;
+      double t = a.u0[i];
+      if (P.rescale_u0) {
+        double Mv, Cv;
+        gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
+        t = __dadd_rn(Mv, t);  // M*u0 + u0
+      }
+      a.U[0][i] = t;
+      loc[0] += t * t;
+    }
+    CLP_PUBLISH();
+    CLP_BAR_CHECK();
+    CLP_REDUCE();
+    // u /= u.norm(), then Mhat u, Chat u for the initial d
+    st.mode = STAGE_DIV; st.srcA = a.U[0]; st.z = vals[0]; st.dst = a.U[1];
+    matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec;
+    cur = 1;
+    CLP_BAR_CHECK();
+  }
+
+  // ---- combine for the initial iterate + initial d (clipper.cpp:201-209) ------------------
+  {
+    double sumu = 0.0;
+    for (int s = 0; s < p.NSEG; ++s) sumu += __ldcg(a.segsum + s);
+    sum_cur = sumu;
+    CLP_ZERO_LOC();
+    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+      const int i = mv.row0 + lr;
+      double Mv, Cv;
+      gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
+      a.MV[cur][i] = Mv; a.CV[cur][i] = Cv;
+      const double ui = a.U[cur][i];
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sumu), Cv), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += __dadd_rn(Mv, ui) / cbu; }
+    }
+    CLP_PUBLISH();
+    CLP_BAR_CHECK();
+    CLP_REDUCE();
+    if (vals[0] > 0.0) d = vals[1] / vals[0];
+  }
+
+  // ---- graduated projected gradient ascent (clipper.cpp:218-281) --------------------------
+  for (i_outer = 0; i_outer < P.maxoliters; ++i_outer) {
+    // gradF and F for the current u under the current d (clipper.cpp:219-220), plus the squared
+    // norm of the first trial point max(u + gradF, 0)
+    CLP_ZERO_LOC();
+    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+      const int i = mv.row0 + lr;
+      const double ui = a.U[cur][i];
+      const double g = grad_entry(ui, sum_cur, a.MV[cur][i], a.CV[cur][i], d);
+      a.Gd[cur][i] = g;
+      loc[0] += ui * g;
+      double w = __dadd_rn(ui, __dmul_rn(1.0, g)); w = (w < 0.0) ? 0.0 : w;
+      loc[1] += w * w;
+    }
+    CLP_PUBLISH();
+    CLP_BAR_CHECK();
+    CLP_REDUCE();
+    F = vals[0];
+    z = vals[1];
+
+    for (int j = 0; j < P.maxiniters; ++j) {
+      double alpha = 1.0;
+      double Fnew = 0.0, deltaF = 0.0, du2 = 0.0, zB = 0.0, sum_trial = sum_cur;
+      const int nxt = cur ^ 1;
+      for (int k = 0; k < P.maxlsiters; ++k) {
+        // Phase A: candidate point + dense pass over M
+        StageArgs st;
+        st.mode = STAGE_STEP; st.srcA = a.U[cur]; st.srcB = a.Gd[cur]; st.alpha = alpha; st.z = z;
+        st.dst = a.U[nxt]; st.segsum = a.segsum;
+        matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec; ++n_evals;
+        CLP_BAR_CHECK();
+        // Phase B: gradFnew, Fnew, |unew-u|^2 and the squared norms of both possible next trials
+        double sumv = 0.0;
+        for (int s = 0; s < p.NSEG; ++s) sumv += __ldcg(a.segsum + s);
+        const double alpha_rej = __dmul_rn(alpha, P.beta);
+        CLP_ZERO_LOC();
+        for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+          const int i = mv.row0 + lr;
+          double Mv, Cv;
+          gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
+          a.MV[nxt][i] = Mv; a.CV[nxt][i] = Cv;
+          const double un = a.U[nxt][i];
+          const double g = grad_entry(un, sumv, Mv, Cv, d);
+          a.Gd[nxt][i] = g;
+          const double uo = a.U[cur][i], go = a.Gd[cur][i];
+          loc[0] += un * g;
+          const double du = __dsub_rn(un, uo);
+          loc[1] += du * du;
+          double wa = __dadd_rn(uo, __dmul_rn(alpha_rej, go)); wa = (wa < 0.0) ? 0.0 : wa;
+          loc[2] += wa * wa;
+          double wb = __dadd_rn(un, __dmul_rn(1.0, g)); wb = (wb < 0.0) ? 0.0 : wb;
+          loc[3] += wb * wb;
+        }
+        CLP_PUBLISH();
+        CLP_BAR_CHECK();
+        CLP_REDUCE();
+        // Phase C: the line-search decision (clipper.cpp:242-251), identical on every CTA
+        Fnew = vals[0]; du2 = vals[1]; zB = vals[3];
+        deltaF = Fnew - F;
+        sum_trial = sumv;
+        if (deltaF < -P.eps) {
+          alpha = alpha_rej;
+          if (k + 1 < P.maxlsiters) { z = vals[2]; continue; }
+        }
+        break;
+      }
+      // accept (also when the line search ran out, clipper.cpp:256-258)
+      const double deltau = sqrt(du2);
+      F = Fnew;
+      cur = nxt;
+      sum_cur = sum_trial;
+      z = zB;
+      ++n_inner;
+      if (deltau < P.tol_u || fabs(deltaF) < P.tol_F) break;
+    }
+
+    // penalty ramp (clipper.cpp:268-280); MV/CV/sum_cur belong to the accepted u
+    CLP_ZERO_LOC();
+    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+      const int i = mv.row0 + lr;
+      const double ui = a.U[cur][i];
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), a.CV[cur][i]), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(a.MV[cur][i], ui) / cbu); }
+    }
+    CLP_PUBLISH();
+    CLP_BAR_CHECK();
+    CLP_REDUCE();
+    if (vals[0] > 0.0) d += vals[1] / vals[0];
+    else break;
+  }
+
+finish:
+  if (status == 0) {
+    for (int lr = gtid; lr < mv.rows; lr += gthreads) a.u_final[mv.row0 + lr] = a.U[cur][mv.row0 + lr];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.out->F = F; a.out->d = d; a.out->ifinal = i_outer; a.out->cur = cur; a.out->status = status;
+    a.out->n_evals = n_evals; a.out->n_inner = n_inner; a.out->n_matvec = n_matvec;
+  }
+#undef CLP_ZERO_LOC
+#undef CLP_PUBLISH
+#undef CLP_REDUCE
+#undef CLP_BAR_CHECK
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: encode / decode between the reference's dense column-major fp64 M, C and the HBM layout
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void fill_neutral_kernel(T* M, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) M[i] = encode<T>(0.0, false);
+}
+
+// Panel of columns [j0, j1) of the column-major inputs (panel-local pointers). Only the strict
+// upper triangle (i<j) is read (clipper.cpp:149-158); both (i,j) and (j,i) are written.
+// flags: bit0 = negative affinity seen, bit1 = constraint value outside {0,1}
+template <typename T>
+__global__ void encode_dense_panel_kernel(const double* Mp, const double* Cp, int m, int j0, int j1,
+                                          T* M, long long ld, int row0, int rows, int* flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = j0 + blockIdx.y;
+  if (j >= j1 || i >= j) return;
+  const double mval = Mp[(size_t)(j - j0) * m + i];
+  const double cval = Cp[(size_t)(j - j0) * m + i];
+  if (mval < 0.0) atomicOr(flags, 1);
+  if (cval != 0.0 && cval != 1.0) atomicOr(flags, 2);
+  const T e = encode<T>(mval, cval != 0.0);
+  if (i >= row0 && i < row0 + rows) M[(size_t)(i - row0) * ld + j] = e;
+  if (j >= row0 && j < row0 + rows) M[(size_t)(j - row0) * ld + i] = e;
+}
+
+// strictly-upper CSC -> HBM layout.  pass 0: M values (sign cleared => C=1 provisional is wrong),
+// so the host runs: fill neutral; pass A writes |M| with C=0 (negative sign); pass B sets C bits.
+template <typename T>
+__global__ void scatter_csc_M_kernel(const long long* colptr, const int* rowidx, const double* val, int m,
+                                     T* M, long long ld, int row0, int rows, int* flags) {
+  const int j = blockIdx.x;
+  for (long long q = colptr[j] + threadIdx.x; q < colptr[j + 1]; q += blockDim.x) {
+    const int i = rowidx[q];
+    if (i < 0 || i >= j) { atomicOr(flags, 4); continue; }
+    const double v = val[q];
+    if (v < 0.0) atomicOr(flags, 1);
+    const T e = encode<T>(v, false);
+    if (i >= row0 && i < row0 + rows) M[(size_t)(i - row0) * ld + j] = e;
+    if (j >= row0 && j < row0 + rows) M[(size_t)(j - row0) * ld + i] = e;
+  }
+}
+template <typename T>
+__global__ void scatter_csc_C_kernel(const long long* colptr, const int* rowidx, const double* val, int m,
+                                     T* M, long long ld, int row0, int rows, int* flags) {
+  const int j = blockIdx.x;
+  for (long long q = colptr[j] + threadIdx.x; q < colptr[j + 1]; q += blockDim.x) {
+    const int i = rowidx[q];
+    if (i < 0 || i >= j) { atomicOr(flags, 4); continue; }
+    const double v = val[q];
+    if (v == 0.0) continue;
+    if (v != 1.0) atomicOr(flags, 2);
+    if (i >= row0 && i < row0 + rows) { T* p = M + (size_t)(i - row0) * ld + j; double a; bool c; decode(*p, a, c); *p = encode<T>(a, true); }
+    if (j >= row0 && j < row0 + rows) { T* p = M + (size_t)(j - row0) * ld + i; double a; bool c; decode(*p, a, c); *p = encode<T>(a, true); }
+  }
+}
+
+// columns [j0,j1) of getAffinityMatrix()/getConstraintMatrix(): out[(j-j0)*m + i], sym + I.
+// By symmetry column j equals row j of the store, so reads are coalesced along i.
+template <typename T>
+__global__ void decode_dense_panel_kernel(const T* M, long long ld, int m, int j0, int j1, int which,
+                                          double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = j0 + blockIdx.y;
+  if (j >= j1 || i >= m) return;
+  double v;
+  if (i == j) v = 1.0;
+  else {
+    double a; bool c;
+    decode(M[(size_t)j * ld + i], a, c);
+    v = which ? (c ? 1.0 : 0.0) : a;
+  }
+  out[(size_t)(j - j0) * m + i] = v;
+}
+
+// count stored affinities / constraints in the strict upper triangle
+template <typename T>
+__global__ void count_upper_kernel(const T* M, long long ld, int m, int row0, int rows,
+                                   unsigned long long* counts) {
+  unsigned long long nM = 0, nC = 0;
+  const size_t total = (size_t)rows * (size_t)m;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int lr = (int)(t / m), j = (int)(t % m);
+    const int i = row0 + lr;
+    if (i >= j) continue;
+    double a; bool c;
+    decode(M[(size_t)lr * ld + j], a, c);
+    nM += (a != 0.0); nC += c;
+  }
+  for (int o = 16; o > 0; o >>= 1) { nM += __shfl_xor_sync(0xffffffffu, nM, o); nC += __shfl_xor_sync(0xffffffffu, nC, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(counts, nM); atomicAdd(counts + 1, nC); }
+}
+
+// k x k sub-block of M induced by the index set S (for Rounding::DSD): out column-major doubles
+template <typename T>
+__global__ void gather_subblock_kernel(const T* M, long long ld, const int* S, int k, double* out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (a >= k || b >= k) return;
+  double v = 0.0;
+  if (a != b) { bool c; decode(M[(size_t)S[b] * ld + S[a]], v, c); }
+  out[(size_t)b * k + a] = v;
+}
+
+}  // namespace clp

@@ -1,0 +1,174 @@
+/*
+ * clipper_b200.h -- C-ABI of the B200-native CLIPPER hot path.
+ *
+ * This is the drop-in seam: a maintainer of mit-acl/clipper binds THESE entry points from
+ * the bodies of clipper::CLIPPER (see INTEGRATION.md and include/clipper/clipper.h, which is
+ * exactly that shell).  Plain pointers and sizes only -- no Eigen, torch or CUDA types.
+ *
+ * Citations (file:line) are relative to the reference tree (mit-acl/clipper v0.2.4).
+ *
+ * Conventions (those of the reference, which is Eigen / column-major):
+ *   D1, D2 : double, d x n, column-major  -> datum k is the d contiguous doubles at D + d*k
+ *            (invariants::Data = Eigen::MatrixXd, include/clipper/invariants/abstract.h:19)
+ *   A      : int32, m x 2, column-major   -> A(:,0) is m contiguous ints, then A(:,1)
+ *            (Association = Eigen::Matrix<int,Dynamic,2>, include/clipper/types.h:18)
+ *   M, C   : double, m x m, column-major, symmetric (Affinity/Constraint, types.h:19-20)
+ *   u0, u  : double, length m
+ * All functions return 0 on success and a CLP_ERR_* code otherwise; clp_last_error() gives
+ * the message.  Nothing in this library aborts, exits or falls back to a CPU path: if no
+ * sm_100-class CUDA device is usable, clp_create() fails.
+ * A handle is not thread-safe (like clipper::CLIPPER); distinct handles are independent.
+ * Calls are synchronous: results are host-visible on return (the *_dev variants, which take
+ * and return device pointers on the handle's stream, only enqueue work unless stated).
+ */
+#ifndef CLIPPER_B200_H_
+#define CLIPPER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLP_OK 0
+#define CLP_ERR_INVALID 1     /* bad argument / shape / state                         */
+#define CLP_ERR_CUDA 2        /* CUDA runtime error (message holds cudaGetErrorString) */
+#define CLP_ERR_ALLOC 3       /* device or host allocation failed                     */
+#define CLP_ERR_UNSUPPORTED 4 /* input outside the supported contract (e.g. M<0, non-binary C) */
+#define CLP_ERR_TIMEOUT 5     /* an in-kernel barrier timed out (hang guard)           */
+#define CLP_ERR_COMM 6        /* peer-memory / multi-GPU set-up error                  */
+
+/* storage type of the dense affinity matrix in HBM */
+#define CLP_STORE_F32 0 /* default: 4 B/entry, the only O(m^2) traffic of the solver   */
+#define CLP_STORE_F64 1 /* 8 B/entry: bit-faithful fp64 affinities (strict-parity mode) */
+
+/* Rounding, reference include/clipper/clipper.h:49-59 */
+#define CLP_ROUND_NONZERO 0
+#define CLP_ROUND_DSD 1
+#define CLP_ROUND_DSD_HEU 2
+
+typedef struct clp_handle_s* clp_handle;
+
+/* POD mirror of clipper::Params, reference include/clipper/clipper.h:27-60 (same defaults) */
+typedef struct clp_params {
+  double tol_u;       /* 1e-8  */
+  double tol_F;       /* 1e-9  */
+  double tol_Fop;     /* 1e-10, declared by the reference but never read by its solver */
+  int32_t maxiniters; /* 200   */
+  int32_t maxoliters; /* 1000  */
+  double beta;        /* 0.25  */
+  int32_t maxlsiters; /* 99    */
+  double eps;         /* 1e-9  */
+  double affinityeps; /* 1e-4  */
+  int32_t rescale_u0; /* 1     */
+  int32_t rounding;   /* CLP_ROUND_DSD_HEU */
+} clp_params;
+
+/* POD mirror of clipper::Solution, reference include/clipper/clipper.h:65-73, plus counters.
+ * u / u0 / nodes are returned through caller-allocated buffers of clp_solve(). */
+typedef struct clp_solution {
+  double t;          /* wall-clock seconds spent in the solve call (Solution::t)            */
+  int32_t ifinal;    /* outer iterations before termination (Solution::ifinal)              */
+  int32_t n_nodes;   /* number of selected nodes (Solution::nodes.size())                   */
+  double score;      /* final objective F (Solution::score)                                 */
+  double d_final;    /* final penalty d                                                      */
+  int64_t n_evals;   /* line-search objective evaluations (clipper.cpp:238-242)              */
+  int64_t n_matvec;  /* dense M passes executed on the device (= n_evals + 2)                */
+  int64_t n_inner;   /* accepted projected-gradient steps                                    */
+  double kernel_ms;  /* device time of the solver kernel, CUDA events on the handle's stream */
+} clp_solution;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  storage: CLP_STORE_*.  Replaces the CLIPPER ctor (clipper.cpp:15-17). */
+int clp_create(int device, int storage, clp_handle* out);
+int clp_destroy(clp_handle h);
+const char* clp_last_error(clp_handle h); /* h may be NULL: error of the last failed clp_create */
+void clp_default_params(clp_params* p);
+int clp_set_params(clp_handle h, const clp_params* p);
+int clp_get_params(clp_handle h, clp_params* p);
+/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL -> handle-owned stream. */
+int clp_set_stream(clp_handle h, void* cuda_stream);
+/* library/compile info: "clipper_b200 <version> sm_100a ..." */
+const char* clp_version(void);
+
+/* ---- K1: scorePairwiseConsistency (clipper.cpp:21-65) ----------------------------------- */
+/* EuclideanDistance (src/invariants/euclidean_distance.cpp:13-31). A==NULL or m==0 ->
+ * all-to-all hypothesis (utils.h:61-71). Host pointers; copies in, builds dense M/C in HBM. */
+int clp_score_euclidean(clp_handle h, const double* D1, int32_t d, int64_t n1, const double* D2,
+                        int64_t n2, const int32_t* A, int64_t m, double sigma, double epsilon,
+                        double mindist);
+/* PointNormalDistance (src/invariants/pointnormal_distance.cpp:13-35); data are 6 x n. */
+int clp_score_pointnormal(clp_handle h, const double* D1, int64_t n1, const double* D2, int64_t n2,
+                          const int32_t* A, int64_t m, double sigp, double epsp, double sign,
+                          double epsn);
+/* Same, inputs already resident in HBM (device pointers, same layouts). A_dev must be given. */
+int clp_score_euclidean_dev(clp_handle h, const double* D1_dev, int32_t d, int64_t n1,
+                            const double* D2_dev, int64_t n2, const int32_t* A_dev, int64_t m,
+                            double sigma, double epsilon, double mindist);
+int clp_score_pointnormal_dev(clp_handle h, const double* D1_dev, int64_t n1, const double* D2_dev,
+                              int64_t n2, const int32_t* A_dev, int64_t m, double sigp, double epsp,
+                              double sign, double epsn);
+
+/* ---- K7: matrix get/set (clipper.cpp:131-166) -------------------------------------------- */
+/* setMatrixData: strict upper triangle of the column-major m x m inputs is used, diagonal and
+ * lower triangle ignored (clipper.cpp:149-158). Contract: M >= 0, C in {0,1} (clipper.h:166-176). */
+int clp_set_dense(clp_handle h, const double* M, const double* C, int64_t m);
+/* setSparseMatrixData: strictly-upper CSC (column-major compressed) of M and of C (clipper.h:137). */
+int clp_set_sparse_upper(clp_handle h, int64_t m, const int64_t* colptrM, const int32_t* rowidxM,
+                         const double* valM, const int64_t* colptrC, const int32_t* rowidxC,
+                         const double* valC);
+/* getAffinityMatrix (which=0) / getConstraintMatrix (which=1): sym + I, column-major m x m. */
+int clp_get_dense(clp_handle h, int which, double* out);
+int clp_num_associations(clp_handle h, int64_t* m);
+/* getInitialAssociations (clipper.cpp:117-120): column-major m x 2; error if none were scored. */
+int clp_get_associations(clp_handle h, int32_t* A);
+/* number of stored affinities (i<j, M_ij != 0) and constraints (C_ij = 1), for density reports */
+int clp_count_nonzeros(clp_handle h, int64_t* nnzM_upper, int64_t* nnzC_upper);
+
+/* ---- K2..K6: solve (clipper.cpp:69-78,172-323) -------------------------------------------- */
+/* u0: m doubles or NULL (then U[0,1) from std::random_device like utils.cpp:22-29).
+ * u_out (m doubles), u0_out (m doubles) and nodes_out (m int32) may be NULL.
+ * Rounding NONZERO and DSD_HEU run on the device-produced u exactly as utils.cpp:33-68;
+ * DSD pulls the support(u) sub-block of M and runs an exact densest-subgraph on the host. */
+int clp_solve(clp_handle h, const double* u0, clp_solution* out, double* u_out, int32_t* nodes_out,
+              double* u0_out);
+/* u0 resident in HBM (device pointer, required). u_out_dev (device, m doubles) may be NULL.
+ * Blocking: the solution scalars and nodes are host-visible on return. */
+int clp_solve_dev(clp_handle h, const double* u0_dev, clp_solution* out, double* u_out_dev,
+                  int32_t* nodes_out);
+
+/* ---- K2 exposed: one penalised mat-vec ------------------------------------------------- */
+/* y = (1+d) v - d (sum v) 1 + Mhat v + d Chat v  == Md v with Md = M - d(11' - C), unit
+ * diagonals (clipper.cpp:219; matlab/clipper.m:69-70,93).  Mv/Cv (may be NULL) receive the
+ * off-diagonal products Mhat v and Chat v.  Host pointers. */
+int clp_matvec(clp_handle h, const double* v, double d, double* y, double* Mv, double* Cv);
+/* Device pointers; enqueues reps back-to-back launches on the handle's stream and reports the
+ * mean device time per launch in *ms_per_launch (CUDA events).  Used by the c5 sweep. */
+int clp_matvec_dev(clp_handle h, const double* v_dev, double d, double* y_dev, double* Mv_dev,
+                   double* Cv_dev, int reps, double* ms_per_launch);
+
+/* ---- utils kept callable from the host shell (src/utils.cpp) ------------------------------ */
+void clp_k2ij(uint64_t k, uint64_t n, uint64_t* i, uint64_t* j);        /* utils.cpp:87-97  */
+void clp_create_all_to_all(int64_t n1, int64_t n2, int32_t* A_colmajor); /* utils.h:61-71    */
+int32_t clp_find_k_largest(const double* x, int64_t n, int32_t k, int32_t* out); /* utils.cpp:33-55 */
+int32_t clp_find_above(const double* x, int64_t n, double thr, int32_t* out);    /* utils.cpp:59-68 */
+/* exact densest subgraph restricted to S (dsd.cpp:274-320); A is dense column-major n x n */
+int32_t clp_dsd_dense(const double* A, int64_t n, const int32_t* S, int32_t nS, int32_t* out);
+
+/* ---- multi-GPU: row-block sharding, one process per GPU --------------------------------- */
+/* Declare this handle to be shard `rank` of `world` (rows [rank*m/world, ...) of M live here).
+ * Must be called before scoring. Peer buffers are exchanged as opaque IPC blobs by the caller
+ * (torch.distributed in clipper_b200/distributed.py). */
+int clp_shard_config(clp_handle h, int rank, int world);
+int clp_shard_export(clp_handle h, void* blob, int64_t blob_bytes, int64_t* written);
+int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, int world);
+int64_t clp_shard_blob_bytes(void);
+/* solve() on a sharded handle: every rank calls it collectively with the same u0 (device
+ * pointer); one persistent kernel per GPU, partial products exchanged through peer memory. */
+int clp_shard_solve(clp_handle h, const double* u0_dev, clp_solution* out, double* u_out_dev,
+                    int32_t* nodes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPPER_B200_H_ */
