@@ -234,12 +234,13 @@ def run_ours(args):
     sampler = ClockSampler(local_rank); sampler.start()
     time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, n_matvec, evals = [], [], []
+    kernel_ms, n_matvec, evals, prof = [], [], [], []
     torch.cuda.synchronize()
     ev0.record(stream)
     for _ in range(args.steps):
         step_dev()
         kernel_ms.append(sol.kernel_ms); n_matvec.append(sol.n_matvec); evals.append(sol.n_evals)
+        prof.append((sol.prof_matvec_ms, sol.prof_combine_ms, sol.prof_exchange_ms))
     ev1.record(stream)
     torch.cuda.synchronize()
     dev_ms = ev0.elapsed_time(ev1)
@@ -295,7 +296,9 @@ def run_ours(args):
                                % (args.workload, m, cfg["sigma"], cfg["epsilon"]),
                    "l2": "inputs larger than L2 (dense M = %.2f GB vs 126 MB L2)" % (esz * m * m / 1e9),
                    "evals_per_solve": float(np.mean(evals)), "matvec_per_solve": float(np.mean(n_matvec)),
-                   "solver_kernel_ms": kms, "matvec_alone_gbs": mv_gbs, "matvec_alone_ms": ms_mv.value,
+                   "solver_kernel_ms": kms,
+                   "solver_phase_ms": dict(zip(("dense_passes", "combine", "exchange"), np.mean(prof, axis=0).tolist())),
+                   "matvec_alone_gbs": mv_gbs, "matvec_alone_ms": ms_mv.value,
                    "matvec_alone_frac": mv_gbs / peak, "F": F_dev, "n_nodes": len(nodes_dev)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

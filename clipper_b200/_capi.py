@@ -23,8 +23,8 @@ SYMBOLS = [
     "clp_get_associations", "clp_count_nonzeros",
     "clp_solve", "clp_solve_dev", "clp_matvec", "clp_matvec_dev",
     "clp_k2ij", "clp_create_all_to_all", "clp_find_k_largest", "clp_find_above", "clp_dsd_dense",
-    "clp_shard_config", "clp_shard_export", "clp_shard_import", "clp_shard_blob_bytes",
-    "clp_shard_solve",
+    "clp_shard_config", "clp_shard_rows", "clp_shard_export", "clp_shard_import", "clp_shard_blob_bytes",
+    "clp_set_ctas_per_sm",
 ]
 
 
@@ -46,6 +46,7 @@ class ClpSolution(C.Structure):
         ("score", C.c_double), ("d_final", C.c_double),
         ("n_evals", C.c_int64), ("n_matvec", C.c_int64), ("n_inner", C.c_int64),
         ("kernel_ms", C.c_double),
+        ("prof_matvec_ms", C.c_double), ("prof_combine_ms", C.c_double), ("prof_exchange_ms", C.c_double),
     ]
 
 
@@ -105,7 +106,8 @@ def load():
     L.clp_shard_blob_bytes.restype = i64
     L.clp_shard_export.argtypes = [vp, vp, i64, lp]
     L.clp_shard_import.argtypes = [vp, vp, i64, C.c_int]
-    L.clp_shard_solve.argtypes = [vp, vp, C.POINTER(ClpSolution), vp, ip]
+    L.clp_shard_rows.argtypes = [i64, C.c_int, C.c_int, lp, lp]; L.clp_shard_rows.restype = None
+    L.clp_set_ctas_per_sm.argtypes = [vp, C.c_int]
     _lib = L
     return L
 

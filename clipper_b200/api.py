@@ -250,6 +250,7 @@ class Solution:
         self.n_matvec = 0
         self.n_inner = 0
         self.kernel_ms = 0.0
+        self.prof_ms = (0.0, 0.0, 0.0)  # in-kernel split: dense passes, combine loops, exchange
 
     def __repr__(self):
         return "<CLIPPER Solution>"
@@ -378,6 +379,7 @@ class CLIPPER:
         out.u0, out.u = u0_used, u
         out.d_final, out.n_evals, out.n_matvec, out.n_inner, out.kernel_ms = (
             s.d_final, s.n_evals, s.n_matvec, s.n_inner, s.kernel_ms)
+        out.prof_ms = (s.prof_matvec_ms, s.prof_combine_ms, s.prof_exchange_ms)
         self._soln = out
 
     def solve_as_maximum_clique(self, params=None):

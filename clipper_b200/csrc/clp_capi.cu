@@ -15,6 +15,7 @@
 #include <random>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #ifndef CLP_VERSION
 #define CLP_VERSION "0.1.0"
@@ -55,6 +56,14 @@ struct clp_handle_s {
 
   // sharding (row block [row0,row0+rows) of the m x m matrix lives here)
   int rank = 0, world = 1;
+  DevBuf comm;                          // CommBlock, mapped into every peer
+  uint4* peer_ll[kMaxPeers] = {};       // every rank's LL block
+  CommBlock* peer_comm[kMaxPeers] = {};
+  bool peer_opened[kMaxPeers] = {};     // pointers obtained with cudaIpcOpenMemHandle
+  void* peer_open_ptr[kMaxPeers][2] = {};
+  bool shard_ready = false;
+  unsigned long long seq = 0;           // exchange sequence number (monotonic across solves)
+  void* exported_ll = nullptr;          // llbuf.p at export time (peers hold this mapping)
 
   // problem
   long long m = 0;
@@ -69,7 +78,8 @@ struct clp_handle_s {
   DevBuf E1, E2, D1dev, D2dev;
 
   // solver workspace
-  DevBuf vecs;    // 8 x mpad doubles: U0 U1 G0 G1 MV0 MV1 CV0 CV1
+  DevBuf vecs;    // V_SLOTS x mpad doubles: U0 U1 MV0 MV1 CV0 CV1 (local only)
+  DevBuf llbuf;   // L_SLOTS x mpad LL cells (16 B): X G0 G1 -- replicated across shards via peer stores
   DevBuf parts;   // partM | partC : 2 x NSEG x rows_pad
   DevBuf small;   // segsum[kMaxSeg] | red[2][G][kRedVals]
   DevBuf result;  // SolverOut (256 B) | u_final[mpad]
@@ -111,9 +121,6 @@ int ensure_pinned(clp_handle h, size_t bytes) {
   return CLP_OK;
 }
 
-// unsigned long long counter | int error | int flags | u64 counts[2]
-struct SyncBlock { unsigned long long counter; int error; int flags; unsigned long long counts[2]; };
-
 void shard_rows(long long m, int rank, int world, int* row0, int* rows) {
   // row tiles of 32 are never split between shards
   const long long tiles = (m + kRowTile - 1) / kRowTile;
@@ -154,7 +161,15 @@ int ensure_matrix(clp_handle h, long long m) {
   CLP_CUDA(h, h->Mbuf.ensure((size_t)h->rows_pad * (size_t)h->ld * h->esize()));
   h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_per_sm);
   // workspace
-  CLP_CUDA(h, h->vecs.ensure((size_t)8 * h->mpad * sizeof(double)));
+  CLP_CUDA(h, h->vecs.ensure((size_t)V_SLOTS * h->mpad * sizeof(double)));
+  {
+    void* before = h->llbuf.p;
+    CLP_CUDA(h, h->llbuf.ensure((size_t)L_SLOTS * h->mpad * sizeof(uint4)));
+    if (h->llbuf.p != before) {  // fresh cells carry tag 0 == "never written"
+      CLP_CUDA(h, cudaMemset(h->llbuf.p, 0, h->llbuf.cap));
+      h->shard_ready = false;
+    }
+  }
   CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
   CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
   CLP_CUDA(h, h->result.ensure(256 + (size_t)h->mpad * sizeof(double)));
@@ -272,7 +287,8 @@ int launch_matvec(clp_handle h, const StageArgs& st, const double* v, double d, 
 
 int matvec_enqueue(clp_handle h, const double* v_dev, double d, double* y_dev, double* Mv_dev, double* Cv_dev) {
   StageArgs st;
-  st.mode = STAGE_RAW; st.srcA = v_dev; st.srcB = nullptr; st.alpha = 0.0; st.z = 1.0; st.dst = nullptr;
+  st.mode = STAGE_RAW; st.srcA = v_dev; st.llA = nullptr; st.llB = nullptr; st.tag = 0;
+  st.error = &h->sync.as<SyncBlock>()->error; st.alpha = 0.0; st.z = 1.0; st.dst = nullptr;
   st.segsum = h->small.as<double>();
   return (h->storage == CLP_STORE_F64) ? launch_matvec<double>(h, st, v_dev, d, y_dev, Mv_dev, Cv_dev)
                                        : launch_matvec<float>(h, st, v_dev, d, y_dev, Mv_dev, Cv_dev);
@@ -293,7 +309,6 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
                std::chrono::steady_clock::time_point t_begin) {
   const clp_params& P = h->prm;
   if (P.maxlsiters < 1) return fail(h, CLP_ERR_INVALID, "maxlsiters must be >= 1");
-  if (h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "sharded solve goes through clp_shard_solve");
   SolverArgs a;
   a.mv = mat_view(h);
   a.plan = h->plan;
@@ -301,17 +316,24 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   a.prm.maxiniters = P.maxiniters; a.prm.maxoliters = P.maxoliters; a.prm.maxlsiters = P.maxlsiters;
   a.prm.rescale_u0 = P.rescale_u0 ? 1 : 0;
   SyncBlock* sb = h->sync.as<SyncBlock>();
-  a.bar.counter = &sb->counter; a.bar.error = &sb->error; a.bar.nblocks = (unsigned)h->plan.G;
+  a.bar.sb = sb; a.bar.nleaf = h->plan.SG; a.bar.leafsize = h->plan.RG;
   a.u0 = h->u0dev.as<double>();
-  double* v = h->vecs.as<double>();
-  a.U[0] = v; a.U[1] = v + h->mpad; a.Gd[0] = v + 2 * h->mpad; a.Gd[1] = v + 3 * h->mpad;
-  a.MV[0] = v + 4 * h->mpad; a.MV[1] = v + 5 * h->mpad; a.CV[0] = v + 6 * h->mpad; a.CV[1] = v + 7 * h->mpad;
+  a.vecs = h->vecs.as<double>();
+  a.ll = h->llbuf.as<uint4>();
+  a.mpad = h->mpad;
   a.partM = h->parts.as<double>();
   a.partC = a.partM + (size_t)h->plan.NSEG * h->rows_pad;
   a.segsum = h->small.as<double>();
   a.red = h->small.as<double>() + kMaxSeg;
   a.out = reinterpret_cast<SolverOut*>(h->result.p);
   a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
+  a.rank = h->rank; a.world = h->world; a.seq0 = h->seq;
+  a.comm = h->comm.as<CommBlock>();
+  for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
+  if (h->world > 1) {
+    if (!h->shard_ready || h->exported_ll != h->llbuf.p)
+      return fail(h, CLP_ERR_COMM, "sharded solve: peer buffers not connected (clp_shard_export/import after scoring)");
+  }
 
   if (int rc = reset_sync(h)) return rc;
   CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -327,7 +349,11 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   CLP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 
   const SolverOut so = *reinterpret_cast<const SolverOut*>(h->pinned);
-  if (so.status != 0) return fail(h, CLP_ERR_TIMEOUT, "solver kernel: device-wide barrier timed out");
+  h->seq = so.seq_end;
+  if (so.status != 0) {
+    h->shard_ready = false;  // sequence numbers may have diverged between ranks
+    return fail(h, CLP_ERR_TIMEOUT, "solver kernel: device-wide barrier / peer exchange timed out");
+  }
   const double* u = reinterpret_cast<const double*>(reinterpret_cast<const char*>(h->pinned) + 256);
 
   // rounding (ref clipper.cpp:287-310) on the device-produced u
@@ -345,6 +371,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
     std::vector<int32_t> S((size_t)h->m);
     S.resize((size_t)clp_find_above(u, h->m, 0.0, S.data()));
     const int k = (int)S.size();
+    if (k > 0 && h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "Rounding::DSD on a sharded handle");
     if (k > 0) {
       // ship only the k x k sub-block of M induced by support(u)
       CLP_CUDA(h, h->cscbuf.ensure((size_t)k * sizeof(int32_t) + (size_t)k * k * sizeof(double) + 16));
@@ -373,6 +400,9 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   if (out) {
     out->ifinal = so.ifinal; out->n_nodes = (int32_t)nodes.size(); out->score = so.F; out->d_final = so.d;
     out->n_evals = so.n_evals; out->n_matvec = so.n_matvec; out->n_inner = so.n_inner; out->kernel_ms = ms;
+    out->prof_matvec_ms = 1e-6 * (double)so.ns_matvec; out->prof_combine_ms = 1e-6 * (double)so.ns_combine;
+    out->prof_exchange_ms = 1e-6 * (double)so.ns_exchange;
+
     out->t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   }
   return CLP_OK;
@@ -436,7 +466,10 @@ int clp_create(int device, int storage, clp_handle* out) {
 int clp_destroy(clp_handle h) {
   if (!h) return CLP_OK;
   cudaSetDevice(h->device);
-  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->parts, &h->small,
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
+  h->comm.release();
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->parts, &h->small,
                     &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -691,14 +724,104 @@ int clp_matvec_dev(clp_handle h, const double* v_dev, double d, double* y_dev, d
 }
 
 // ---- multi-GPU (row-block sharding) --------------------------------------------------------
+namespace {
+struct ShardBlob {  // opaque to the caller; 256 bytes
+  cudaIpcMemHandle_t ll;     // 64 B  (LL-cell block)
+  cudaIpcMemHandle_t comm;   // 64 B
+  unsigned long long pid;
+  void* ll_ptr;              // valid only inside the exporting process (same-process peers)
+  void* comm_ptr;
+  long long mpad;
+  int rank, world, device, pad;
+};
+static_assert(sizeof(ShardBlob) <= 256, "blob too large");
+}  // namespace
+
 int clp_shard_config(clp_handle h, int rank, int world) {
-  if (!h || world < 1 || rank < 0 || rank >= world) return CLP_ERR_INVALID;
-  h->rank = rank; h->world = world; h->has_matrix = false;
+  if (!h || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(h, CLP_ERR_INVALID, "bad shard configuration (1 <= world <= 8)");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  h->rank = rank; h->world = world; h->has_matrix = false; h->shard_ready = false; h->seq = 0;
+  CLP_CUDA(h, h->comm.ensure(sizeof(CommBlock)));
+  CLP_CUDA(h, cudaMemset(h->comm.p, 0, sizeof(CommBlock)));
   return CLP_OK;
 }
+
+void clp_shard_rows(int64_t m, int rank, int world, int64_t* row0, int64_t* rows) {
+  int r0 = 0, n = 0;
+  shard_rows(m, rank, world, &r0, &n);
+  if (row0) *row0 = r0;
+  if (rows) *rows = n;
+}
+
 int64_t clp_shard_blob_bytes(void) { return 256; }
-int clp_shard_export(clp_handle h, void*, int64_t, int64_t*) { return fail(h, CLP_ERR_UNSUPPORTED, "peer-memory solver not built yet"); }
-int clp_shard_import(clp_handle h, const void*, int64_t, int) { return fail(h, CLP_ERR_UNSUPPORTED, "peer-memory solver not built yet"); }
-int clp_shard_solve(clp_handle h, const double*, clp_solution*, double*, int32_t*) { return fail(h, CLP_ERR_UNSUPPORTED, "peer-memory solver not built yet"); }
+
+int clp_shard_export(clp_handle h, void* blob, int64_t blob_bytes, int64_t* written) {
+  if (!h || !blob || blob_bytes < 256) return CLP_ERR_INVALID;
+  if (h->world < 2) return fail(h, CLP_ERR_INVALID, "clp_shard_export on an unsharded handle");
+  if (!h->llbuf.p) return fail(h, CLP_ERR_INVALID, "clp_shard_export before the first scoring / set call");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  ShardBlob b;
+  std::memset(&b, 0, sizeof(b));
+  CLP_CUDA(h, cudaIpcGetMemHandle(&b.ll, h->llbuf.p));
+  CLP_CUDA(h, cudaIpcGetMemHandle(&b.comm, h->comm.p));
+  b.pid = (unsigned long long)getpid();
+  b.ll_ptr = h->llbuf.p; b.comm_ptr = h->comm.p; b.mpad = h->mpad;
+  b.rank = h->rank; b.world = h->world; b.device = h->device;
+  std::memset(blob, 0, 256);
+  std::memcpy(blob, &b, sizeof(b));
+  if (written) *written = 256;
+  h->exported_ll = h->llbuf.p;
+  return CLP_OK;
+}
+
+int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, int world) {
+  if (!h || !blobs || blob_bytes_each < 256) return CLP_ERR_INVALID;
+  if (world != h->world) return fail(h, CLP_ERR_INVALID, "clp_shard_import: world size mismatch");
+  CLP_CUDA(h, cudaSetDevice(h->device));
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (h->peer_opened[r]) {
+      cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]);
+      h->peer_opened[r] = false;
+    }
+  for (int r = 0; r < world; ++r) {
+    ShardBlob b;
+    std::memcpy(&b, reinterpret_cast<const char*>(blobs) + (size_t)r * blob_bytes_each, sizeof(b));
+    if (b.rank != r || b.world != world) return fail(h, CLP_ERR_COMM, "clp_shard_import: blobs are not in rank order");
+    if (b.mpad != h->mpad) return fail(h, CLP_ERR_COMM, "clp_shard_import: ranks disagree on the problem size");
+    if (r == h->rank) {
+      h->peer_ll[r] = h->llbuf.as<uint4>(); h->peer_comm[r] = h->comm.as<CommBlock>();
+      continue;
+    }
+    if (b.pid == (unsigned long long)getpid()) {  // peer handle lives in this process: plain P2P
+      if (b.device != h->device) {
+        int can = 0;
+        CLP_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, b.device));
+        if (!can) return fail(h, CLP_ERR_COMM, "no P2P access between the shards' devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CLP_CUDA(h, e);
+        cudaGetLastError();
+      }
+      h->peer_ll[r] = reinterpret_cast<uint4*>(b.ll_ptr);
+      h->peer_comm[r] = reinterpret_cast<CommBlock*>(b.comm_ptr);
+    } else {
+      void *pv = nullptr, *pc = nullptr;
+      CLP_CUDA(h, cudaIpcOpenMemHandle(&pv, b.ll, cudaIpcMemLazyEnablePeerAccess));
+      CLP_CUDA(h, cudaIpcOpenMemHandle(&pc, b.comm, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_ll[r] = reinterpret_cast<uint4*>(pv);
+      h->peer_comm[r] = reinterpret_cast<CommBlock*>(pc);
+      h->peer_opened[r] = true; h->peer_open_ptr[r][0] = pv; h->peer_open_ptr[r][1] = pc;
+    }
+  }
+  h->shard_ready = true;
+  return CLP_OK;
+}
+
+int clp_set_ctas_per_sm(clp_handle h, int n) {
+  if (!h || n < 1 || n > 2) return fail(h, CLP_ERR_INVALID, "ctas_per_sm must be 1 or 2");
+  h->ctas_per_sm = n;
+  if (h->m > 0) h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_per_sm);
+  return CLP_OK;
+}
 
 }  // extern "C"

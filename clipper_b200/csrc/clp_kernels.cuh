@@ -74,13 +74,26 @@ template <> __device__ __forceinline__ double encode<double>(double mval, bool c
 }
 
 // ------------------------------------------------------------------------------------------
-// device-wide barrier for the persistent kernels (all CTAs co-resident: cooperative launch).
-// Monotonic ticket counter, no reset; bounded spin so a lost CTA can never hang the GPU.
+// device-wide barrier for the persistent kernel (all CTAs co-resident: cooperative launch).
+// Two-level arrival tree (nleaf counters on separate L2 lines, then one root) so that the ~300
+// arrival atomics do not serialise on one address; monotonic round numbers, no reset inside a
+// launch; the LAST CTA to arrive is told so (it performs the global reduction before releasing
+// the others).  Every spin is bounded: a lost CTA / peer can never hang the GPU.
 // ------------------------------------------------------------------------------------------
-struct GridBar {
-  unsigned long long* counter;  // device global, zero-initialised
-  int* error;                   // device global, set to 1 on timeout
-  unsigned int nblocks;
+struct SyncBlock {  // zeroed by the host before every launch
+  unsigned long long leaf[8][16];  // arrival counters, one 128-byte line each
+  unsigned long long root[16];
+  unsigned long long gen[16];      // generation published by the last arriver
+  double bcast[2][kRedVals];       // globally reduced scalars of the current exchange
+  int error;                       // 1: barrier / peer time-out, 2: bad association index
+  int flags;                       // input-contract violations found by the encode kernels
+  unsigned long long counts[2];
+};
+
+struct TreeBar {
+  SyncBlock* sb;
+  int nleaf;     // == Plan::SG
+  int leafsize;  // == Plan::RG   (G = nleaf * leafsize)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -88,24 +101,71 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-__device__ __forceinline__ void grid_barrier(const GridBar& b) {
+// all threads call; returns true (to every thread) on the CTA that completed round `round`
+__device__ __forceinline__ bool bar_arrive(const TreeBar& b, unsigned long long round, int* smem_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int last = 0;
+    __threadfence();
+    unsigned long long old = atomicAdd(&b.sb->leaf[blockIdx.x % b.nleaf][0], 1ULL);
+    if (old + 1ULL == round * (unsigned long long)b.leafsize) {
+      __threadfence();
+      old = atomicAdd(&b.sb->root[0], 1ULL);
+      if (old + 1ULL == round * (unsigned long long)b.nleaf) { last = 1; __threadfence(); }
+    }
+    *smem_flag = last;
+  }
+  __syncthreads();
+  return *smem_flag != 0;
+}
+__device__ __forceinline__ void bar_release(const TreeBar& b, unsigned long long round) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned long long old = atomicAdd(b.counter, 1ULL);
-    const unsigned long long target = (old / b.nblocks + 1ULL) * b.nblocks;
+    st_release_u64(&b.sb->gen[0], round);
+  }
+}
+__device__ __forceinline__ void bar_wait(const TreeBar& b, unsigned long long round) {
+  if (threadIdx.x == 0) {
     const long long t0 = clock64();
-    while (ld_acquire_u64(b.counter) < target) {
-      __nanosleep(32);
-      if (clock64() - t0 > 4000000000LL) {  // ~2 s: give up, flag, fall through
-        atomicExch(b.error, 1);
-        break;
-      }
+    while (ld_acquire_u64(&b.sb->gen[0]) < round) {
+      __nanosleep(20);
+      if (clock64() - t0 > 4000000000LL) { atomicExch(&b.sb->error, 1); break; }  // ~2 s
     }
     __threadfence();
   }
   __syncthreads();
+}
+__device__ __forceinline__ void grid_barrier(const TreeBar& b, unsigned long long round, int* smem_flag) {
+  if (bar_arrive(b, round, smem_flag)) bar_release(b, round);
+  else bar_wait(b, round);
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// "LL" cells for everything that crosses NVLink: a double travels as one 16-byte store
+// {lo32, tag, hi32, tag}.  The reader spins until both tags equal the expected sequence number,
+// so the datum validates itself -- no system-scope fence, no separate flag, write order free.
+// (8-byte halves are written atomically; the tag is unique per exchange step.)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned tag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ double ll_load(const uint4* p, unsigned tag, int* error) {
+  unsigned lo, t1, hi, t2;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+    if (t1 == tag && t2 == tag) break;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); break; }
+  }
+  return __hiloint2double((int)hi, (int)lo);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -291,8 +351,11 @@ template <> __device__ __forceinline__ int vs_pos<double>(int c) { return c; }
 
 struct StageArgs {
   int mode;            // StageMode
-  const double* srcA;  // RAW/DIV: the vector; STEP: u
-  const double* srcB;  // STEP: gradF
+  const double* srcA;  // RAW: the vector; STEP: u
+  const uint4* llA;    // DIV: the un-normalised vector, LL cells
+  const uint4* llB;    // STEP: gradF, LL cells
+  unsigned tag;        // expected tag of the LL cells
+  int* error;          // time-out flag for LL reads
   double alpha;        // STEP
   double z;            // DIV/STEP: squared norm of the un-normalised vector
   double* dst;         // where the segment owner writes the staged (normalised) vector, or null
@@ -304,8 +367,8 @@ struct StageArgs {
 //   DIV : u /= u.norm()                                            (clipper.cpp:198)
 __device__ __forceinline__ double staged_value(const StageArgs& s, int j, double nrm) {
   if (s.mode == STAGE_RAW) return s.srcA[j];
-  if (s.mode == STAGE_DIV) return s.srcA[j] / nrm;
-  double w = __dadd_rn(s.srcA[j], __dmul_rn(s.alpha, s.srcB[j]));
+  if (s.mode == STAGE_DIV) return ll_load(s.llA + j, s.tag, s.error) / nrm;
+  double w = __dadd_rn(s.srcA[j], __dmul_rn(s.alpha, ll_load(s.llB + j, s.tag, s.error)));
   w = (w < 0.0) ? 0.0 : w;
   return (s.z > 0.0) ? w / nrm : w;
 }
@@ -438,13 +501,16 @@ __device__ void matvec_phase(const MatView& mv, const Plan& p, const StageArgs& 
   const int sg = blockIdx.x % p.SG, rg = blockIdx.x / p.SG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int seg = sg; seg < p.NSEG; seg += p.SG) {
+    // the last segment is ragged: never sweep past the leading dimension (ld = round_up(m,128))
+    const long long rem = mv.ld - (long long)seg * p.W;
+    const int wseg = rem < (long long)p.W ? (rem > 0 ? (int)rem : 0) : p.W;
     stage_segment<T>(st, p, mv.m, seg, rg == 0, vs, red_smem);
     for (int rt = rg; rt < p.NRT; rt += p.RG) {
       const int lr = rt * kRowTile + warp * kRowsPerWarp;
       double accM[kRowsPerWarp], accC[kRowsPerWarp];
 #pragma unroll
       for (int r = 0; r < kRowsPerWarp; ++r) { accM[r] = 0.0; accC[r] = 0.0; }
-      RowSweep<T>::run(mv, lr, seg * p.W, p.W, vs, accM, accC);
+      RowSweep<T>::run(mv, lr, seg * p.W, wseg, vs, accM, accC);
 #pragma unroll
       for (int r = 0; r < kRowsPerWarp; ++r) { accM[r] = warp_sum(accM[r]); accC[r] = warp_sum(accC[r]); }
       if (lane == 0) {
@@ -505,8 +571,23 @@ __global__ void matvec_combine_kernel(MatView mv, Plan p, const double* partM, c
 }
 
 // ------------------------------------------------------------------------------------------
-// K3-K5: the persistent solver
+// K3-K5: the persistent solver (single GPU, or one rank of a row-block-sharded multi-GPU solve)
+//
+// Multi-GPU: rank r owns rows [row0,row0+rows) of M and runs this same kernel.  All
+// O(m) vectors are replicated.  One exchange step per objective evaluation, done INSIDE the
+// kernel over NVLink peer memory (no host, no NCCL launch in the loop):
+//   * the gradient entries of the local rows are stored straight into every peer's copy of the
+//     vector (P2P st.global), while the candidate u is re-derived locally by every rank;
+//   * each rank's partial sums (F, |du|^2, trial norms, ramp statistics) go to every peer's
+//     CommBlock, followed by a release flag; every rank adds the per-rank partials in rank order,
+//     so all ranks take bit-identical decisions with no broadcast and no rank-0 control.
 // ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+
+struct CommBlock {  // lives in each rank's HBM, mapped into every peer (CUDA IPC)
+  uint4 xred[2][kMaxPeers][kRedVals];  // LL cells: per-rank partial sums, double-buffered
+};
+
 struct SolverParams {  // clipper::Params, ref clipper.h:27-60
   double tol_u, tol_F, beta, eps;
   int maxiniters, maxoliters, maxlsiters, rescale_u0;
@@ -516,27 +597,51 @@ struct SolverOut {  // written by CTA 0 at the end
   double F, d;
   int ifinal, cur, status;
   long long n_evals, n_inner, n_matvec;
+  unsigned long long seq_end;
+  unsigned long long ns_matvec, ns_combine, ns_exchange;  // CTA 0's view (globaltimer)
 };
+
+enum VecSlot : int { V_U0 = 0, V_U1 = 1, V_MV0 = 2, V_MV1 = 3, V_CV0 = 4, V_CV1 = 5, V_SLOTS = 6 };
+enum LLSlot : int { L_X = 0, L_G0 = 1, L_G1 = 2, L_SLOTS = 3 };
 
 struct SolverArgs {
   MatView mv;
   Plan plan;
   SolverParams prm;
-  GridBar bar;
+  TreeBar bar;
   const double* u0;  // [m]
-  double* U[2];      // [mpad] current / candidate u
-  double* Gd[2];     // gradF
-  double* MV[2];     // Mhat u
-  double* CV[2];     // Chat u
+  double* vecs;      // V_SLOTS plain vectors, each mpad long (local only)
+  uint4* ll;         // L_SLOTS vectors of LL cells, each mpad long (replicated on every rank)
+  long long mpad;
   double* partM;     // [NSEG][rows_pad]
   double* partC;
   double* segsum;    // [NSEG]
-  double* red;       // [2][G][kRedVals]  (double-buffered: publish/reduce alternate tables)
-  double* u_final;   // [m] copy of the final iterate (local rows)
+  double* red;       // [2][G][kRedVals]  per-CTA partial sums, double-buffered
+  double* u_final;   // [m] copy of the final iterate
   SolverOut* out;
+  // row-block sharding
+  int rank, world;
+  uint4* peer_ll[kMaxPeers];        // every rank's LL block (peer_ll[rank] == ll)
+  CommBlock* comm;                  // local
+  CommBlock* peer_comm[kMaxPeers];  // every rank's CommBlock (peer_comm[rank] == comm)
+  unsigned long long seq0;          // exchange sequence number before this launch
 };
 
-// every CTA reduces the per-CTA partial table in the same fixed order -> identical scalars
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// store one vector entry into the local AND every peer's replica (self-validating LL cell)
+__device__ __forceinline__ void store_replicated(const SolverArgs& a, int slot, int i, double v, unsigned tag) {
+  const size_t off = (size_t)slot * a.mpad + i;
+  ll_store(a.ll + off, v, tag);
+  for (int r = 0; r < a.world; ++r)
+    if (r != a.rank) ll_store(a.peer_ll[r] + off, v, tag);
+}
+
+// one CTA reduces the per-CTA partial table in a fixed order
 __device__ void reduce_table(const double* red, int G, double (&vals)[kRedVals], double* smem /*[kWarps*kRedVals]*/) {
   double loc[kRedVals];
 #pragma unroll
@@ -582,10 +687,63 @@ __device__ void publish_partials(const double (&loc)[kRedVals], double* red, dou
   }
 }
 
+// Global sum of the per-thread partials `loc` over every CTA of every rank; result in `vals`,
+// bit-identical on all CTAs of all ranks.  The last CTA to reach the barrier reduces the local
+// table, (multi-GPU) trades the rank totals with the peers through LL cells and adds them in rank
+// order, publishes the 8 scalars and only then releases the other CTAs.
+// Returns false on a barrier / peer time-out.
+__device__ bool exchange_sums(const SolverArgs& a, const double (&loc)[kRedVals], double (&vals)[kRedVals],
+                              int& red_par, unsigned long long& round, unsigned long long& seq,
+                              double* red_smem, int* smem_flag) {
+  const int G = a.plan.G;
+  SyncBlock* sb = a.bar.sb;
+  double* table = a.red + (size_t)red_par * G * kRedVals;
+  publish_partials(loc, table, red_smem);
+  ++round;
+  ++seq;
+  if (bar_arrive(a.bar, round, smem_flag)) {
+    reduce_table(table, G, vals, red_smem);
+    if (a.world > 1) {
+      const unsigned tag = (unsigned)seq;
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < kRedVals; ++q) red_smem[q] = vals[q];
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < a.world * kRedVals) {  // thread (r,q): send total q to rank r, then fetch rank r's total q
+        const int r = threadIdx.x / kRedVals, q = threadIdx.x % kRedVals;
+        ll_store(&a.peer_comm[r]->xred[red_par][a.rank][q], red_smem[q], tag);
+        red_smem[kRedVals + threadIdx.x] = ll_load(&a.comm->xred[red_par][r][q], tag, &sb->error);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kRedVals; ++q) {
+        double t = 0.0;
+        for (int r = 0; r < a.world; ++r) t += red_smem[kRedVals + r * kRedVals + q];
+        vals[q] = t;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int q = 0; q < kRedVals; ++q) sb->bcast[red_par][q] = vals[q];
+    }
+    bar_release(a.bar, round);
+  } else {
+    bar_wait(a.bar, round);
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) vals[q] = __ldcg(&sb->bcast[red_par][q]);
+  }
+  __syncthreads();
+  red_par ^= 1;
+  return *reinterpret_cast<volatile int*>(&sb->error) == 0;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   __shared__ __align__(16) double vs[kSegMax];
-  __shared__ double red_smem[kWarps * kRedVals];
+  __shared__ double red_smem[kWarps * kRedVals + kMaxPeers * kRedVals];
+  __shared__ int smem_flag;
   const MatView& mv = a.mv;
   const Plan& p = a.plan;
   const SolverParams& P = a.prm;
@@ -593,37 +751,49 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   const int gthreads = p.G * kThreads;
   double vals[kRedVals];
   double loc[kRedVals];
+  double* const U[2] = {a.vecs + (size_t)V_U0 * a.mpad, a.vecs + (size_t)V_U1 * a.mpad};
+  double* const MV[2] = {a.vecs + (size_t)V_MV0 * a.mpad, a.vecs + (size_t)V_MV1 * a.mpad};
+  double* const CV[2] = {a.vecs + (size_t)V_CV0 * a.mpad, a.vecs + (size_t)V_CV1 * a.mpad};
+  const uint4* const GL[2] = {a.ll + (size_t)L_G0 * a.mpad, a.ll + (size_t)L_G1 * a.mpad};
+  int* const errp = &a.bar.sb->error;
 
   long long n_evals = 0, n_inner = 0, n_matvec = 0;
-  int cur = 0;  // U[cur], Gd[cur], MV[cur], CV[cur] describe the current iterate
+  int cur = 0;  // U[cur], G[cur], MV[cur], CV[cur] describe the current iterate
   double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0;
   int i_outer = 0;
   int status = 0;
-
-  // The partial-sum table is double-buffered: a CTA may publish round r+1 while a slower CTA
-  // still reduces round r (there is no barrier between a reduce and the next publish).
+  // The partial-sum tables are double-buffered: a CTA may publish round r+1 while a slower CTA
+  // (or rank) still reads round r.
   int red_par = 0;
+  unsigned long long round = 0;     // barrier rounds of this launch
+  unsigned long long seq = a.seq0;  // exchange steps since the shards were connected (LL tags)
+  unsigned tagG[2] = {0u, 0u};      // tag under which G[0] / G[1] were last written
+  unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, tmark = global_ns();
+#define CLP_LAP(acc) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; }
+
 #define CLP_ZERO_LOC()            \
   _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
-#define CLP_PUBLISH()                                                                   \
-  publish_partials(loc, a.red + (size_t)red_par * p.G * kRedVals, red_smem);
-#define CLP_REDUCE()                                                                    \
-  reduce_table(a.red + (size_t)red_par * p.G * kRedVals, p.G, vals, red_smem);          \
-  red_par ^= 1;
+#define CLP_EXCHANGE()                                                                      \
+  CLP_LAP(ns_cb);                                                                           \
+  if (!exchange_sums(a, loc, vals, red_par, round, seq, red_smem, &smem_flag)) { status = 5; goto finish; } \
+  CLP_LAP(ns_ex);
 #define CLP_BAR_CHECK()                                               \
-  grid_barrier(a.bar);                                                \
-  if (*reinterpret_cast<volatile int*>(a.bar.error) != 0) { status = 5; goto finish; }
+  ++round;                                                            \
+  grid_barrier(a.bar, round, &smem_flag);                             \
+  if (*reinterpret_cast<volatile int*>(errp) != 0) { status = 5; goto finish; } \
+  CLP_LAP(ns_mv);
 
   // ---- initialisation: one power step (clipper.cpp:193-198) ------------------------------
   {
     StageArgs st;
-    st.srcB = nullptr; st.alpha = 0.0; st.segsum = a.segsum;
+    st.llA = nullptr; st.llB = nullptr; st.tag = 0; st.error = errp; st.alpha = 0.0; st.segsum = a.segsum;
     if (P.rescale_u0) {
       st.mode = STAGE_RAW; st.srcA = a.u0; st.z = 1.0; st.dst = nullptr;
       matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec;
       CLP_BAR_CHECK();
     }
     CLP_ZERO_LOC();
+    const unsigned tagX = (unsigned)(seq + 1);
     for (int lr = gtid; lr < mv.rows; lr += gthreads) {
       const int i = mv.row0 + lr;
       double t = a.u0[i];
@@ -632,14 +802,13 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
         gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
         t = __dadd_rn(Mv, t);  // M*u0 + u0
       }
-      a.U[0][i] = t;
+      store_replicated(a, L_X, i, t, tagX);
       loc[0] += t * t;
     }
-    CLP_PUBLISH();
-    CLP_BAR_CHECK();
-    CLP_REDUCE();
+    CLP_EXCHANGE();
     // u /= u.norm(), then Mhat u, Chat u for the initial d
-    st.mode = STAGE_DIV; st.srcA = a.U[0]; st.z = vals[0]; st.dst = a.U[1];
+    st.mode = STAGE_DIV; st.srcA = nullptr; st.llA = a.ll + (size_t)L_X * a.mpad; st.tag = tagX;
+    st.z = vals[0]; st.dst = U[1];
     matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec;
     cur = 1;
     CLP_BAR_CHECK();
@@ -655,14 +824,12 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
       const int i = mv.row0 + lr;
       double Mv, Cv;
       gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
-      a.MV[cur][i] = Mv; a.CV[cur][i] = Cv;
-      const double ui = a.U[cur][i];
+      MV[cur][i] = Mv; CV[cur][i] = Cv;
+      const double ui = U[cur][i];
       const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sumu), Cv), ui);
       if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += __dadd_rn(Mv, ui) / cbu; }
     }
-    CLP_PUBLISH();
-    CLP_BAR_CHECK();
-    CLP_REDUCE();
+    CLP_EXCHANGE();
     if (vals[0] > 0.0) d = vals[1] / vals[0];
   }
 
@@ -671,18 +838,17 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
     // gradF and F for the current u under the current d (clipper.cpp:219-220), plus the squared
     // norm of the first trial point max(u + gradF, 0)
     CLP_ZERO_LOC();
+    tagG[cur] = (unsigned)(seq + 1);
     for (int lr = gtid; lr < mv.rows; lr += gthreads) {
       const int i = mv.row0 + lr;
-      const double ui = a.U[cur][i];
-      const double g = grad_entry(ui, sum_cur, a.MV[cur][i], a.CV[cur][i], d);
-      a.Gd[cur][i] = g;
+      const double ui = U[cur][i];
+      const double g = grad_entry(ui, sum_cur, MV[cur][i], CV[cur][i], d);
+      store_replicated(a, L_G0 + cur, i, g, tagG[cur]);
       loc[0] += ui * g;
       double w = __dadd_rn(ui, __dmul_rn(1.0, g)); w = (w < 0.0) ? 0.0 : w;
       loc[1] += w * w;
     }
-    CLP_PUBLISH();
-    CLP_BAR_CHECK();
-    CLP_REDUCE();
+    CLP_EXCHANGE();
     F = vals[0];
     z = vals[1];
 
@@ -691,10 +857,10 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
       double Fnew = 0.0, deltaF = 0.0, du2 = 0.0, zB = 0.0, sum_trial = sum_cur;
       const int nxt = cur ^ 1;
       for (int k = 0; k < P.maxlsiters; ++k) {
-        // Phase A: candidate point + dense pass over M
+        // Phase A: candidate point + dense pass over the local rows of M
         StageArgs st;
-        st.mode = STAGE_STEP; st.srcA = a.U[cur]; st.srcB = a.Gd[cur]; st.alpha = alpha; st.z = z;
-        st.dst = a.U[nxt]; st.segsum = a.segsum;
+        st.mode = STAGE_STEP; st.srcA = U[cur]; st.llA = nullptr; st.llB = GL[cur]; st.tag = tagG[cur];
+        st.error = errp; st.alpha = alpha; st.z = z; st.dst = U[nxt]; st.segsum = a.segsum;
         matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec; ++n_evals;
         CLP_BAR_CHECK();
         // Phase B: gradFnew, Fnew, |unew-u|^2 and the squared norms of both possible next trials
@@ -702,15 +868,16 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
         for (int s = 0; s < p.NSEG; ++s) sumv += __ldcg(a.segsum + s);
         const double alpha_rej = __dmul_rn(alpha, P.beta);
         CLP_ZERO_LOC();
+        tagG[nxt] = (unsigned)(seq + 1);
         for (int lr = gtid; lr < mv.rows; lr += gthreads) {
           const int i = mv.row0 + lr;
           double Mv, Cv;
           gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
-          a.MV[nxt][i] = Mv; a.CV[nxt][i] = Cv;
-          const double un = a.U[nxt][i];
+          MV[nxt][i] = Mv; CV[nxt][i] = Cv;
+          const double un = U[nxt][i];
           const double g = grad_entry(un, sumv, Mv, Cv, d);
-          a.Gd[nxt][i] = g;
-          const double uo = a.U[cur][i], go = a.Gd[cur][i];
+          store_replicated(a, L_G0 + nxt, i, g, tagG[nxt]);
+          const double uo = U[cur][i], go = ll_load(GL[cur] + i, tagG[cur], errp);
           loc[0] += un * g;
           const double du = __dsub_rn(un, uo);
           loc[1] += du * du;
@@ -719,10 +886,8 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
           double wb = __dadd_rn(un, __dmul_rn(1.0, g)); wb = (wb < 0.0) ? 0.0 : wb;
           loc[3] += wb * wb;
         }
-        CLP_PUBLISH();
-        CLP_BAR_CHECK();
-        CLP_REDUCE();
-        // Phase C: the line-search decision (clipper.cpp:242-251), identical on every CTA
+        CLP_EXCHANGE();
+        // Phase C: the line-search decision (clipper.cpp:242-251), identical on every CTA / rank
         Fnew = vals[0]; du2 = vals[1]; zB = vals[3];
         deltaF = Fnew - F;
         sum_trial = sumv;
@@ -746,28 +911,32 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
     CLP_ZERO_LOC();
     for (int lr = gtid; lr < mv.rows; lr += gthreads) {
       const int i = mv.row0 + lr;
-      const double ui = a.U[cur][i];
-      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), a.CV[cur][i]), ui);
-      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(a.MV[cur][i], ui) / cbu); }
+      const double ui = U[cur][i];
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), CV[cur][i]), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(MV[cur][i], ui) / cbu); }
     }
-    CLP_PUBLISH();
-    CLP_BAR_CHECK();
-    CLP_REDUCE();
+    CLP_EXCHANGE();
     if (vals[0] > 0.0) d += vals[1] / vals[0];
     else break;
   }
 
-finish:
-  if (status == 0) {
-    for (int lr = gtid; lr < mv.rows; lr += gthreads) a.u_final[mv.row0 + lr] = a.U[cur][mv.row0 + lr];
+  // every rank holds the complete iterate; copy it out, then (multi-GPU) one last rendez-vous so
+  // that no rank starts overwriting a peer's replicas while that peer is still inside this launch
+  for (int i = gtid; i < mv.m; i += gthreads) a.u_final[i] = U[cur][i];
+  if (a.world > 1) {
+    CLP_ZERO_LOC();
+    CLP_EXCHANGE();
   }
+
+finish:
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.out->F = F; a.out->d = d; a.out->ifinal = i_outer; a.out->cur = cur; a.out->status = status;
-    a.out->n_evals = n_evals; a.out->n_inner = n_inner; a.out->n_matvec = n_matvec;
+    a.out->n_evals = n_evals; a.out->n_inner = n_inner; a.out->n_matvec = n_matvec; a.out->seq_end = seq;
+    a.out->ns_matvec = ns_mv; a.out->ns_combine = ns_cb; a.out->ns_exchange = ns_ex;
   }
+#undef CLP_LAP
 #undef CLP_ZERO_LOC
-#undef CLP_PUBLISH
-#undef CLP_REDUCE
+#undef CLP_EXCHANGE
 #undef CLP_BAR_CHECK
 }
 

@@ -76,6 +76,9 @@ typedef struct clp_solution {
   int64_t n_matvec;  /* dense M passes executed on the device (= n_evals + 2)                */
   int64_t n_inner;   /* accepted projected-gradient steps                                    */
   double kernel_ms;  /* device time of the solver kernel, CUDA events on the handle's stream */
+  /* in-kernel phase split seen by CTA 0 (globaltimer): dense passes over M (+ their barrier),
+   * O(m) combine loops, partial-sum exchange (grid barrier + NVLink peer exchange if sharded) */
+  double prof_matvec_ms, prof_combine_ms, prof_exchange_ms;
 } clp_solution;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -155,18 +158,24 @@ int32_t clp_find_above(const double* x, int64_t n, double thr, int32_t* out);   
 /* exact densest subgraph restricted to S (dsd.cpp:274-320); A is dense column-major n x n */
 int32_t clp_dsd_dense(const double* A, int64_t n, const int32_t* S, int32_t nS, int32_t* out);
 
-/* ---- multi-GPU: row-block sharding, one process per GPU --------------------------------- */
-/* Declare this handle to be shard `rank` of `world` (rows [rank*m/world, ...) of M live here).
- * Must be called before scoring. Peer buffers are exchanged as opaque IPC blobs by the caller
- * (torch.distributed in clipper_b200/distributed.py). */
+/* ---- multi-GPU: row-block sharding, one process (or one handle) per GPU ------------------- */
+/* SURVEY 8e.  Rank r of `world` keeps rows [row0,row0+rows) x all columns of M in its HBM
+ * (clp_shard_rows gives the partition; scoring needs no communication).  clp_solve*() then runs
+ * ONE persistent kernel per GPU; the single exchange step per objective evaluation happens inside
+ * that kernel through NVLink peer memory (P2P stores + release/acquire flags), so every rank
+ * must call clp_solve*() collectively with the same u0.  Set-up order on every rank:
+ *   clp_shard_config -> first scoring/set call (allocates) -> clp_shard_export ->
+ *   [caller all-gathers the 256-byte blobs, e.g. torch.distributed] -> clp_shard_import. */
 int clp_shard_config(clp_handle h, int rank, int world);
-int clp_shard_export(clp_handle h, void* blob, int64_t blob_bytes, int64_t* written);
-int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, int world);
+void clp_shard_rows(int64_t m, int rank, int world, int64_t* row0, int64_t* rows);
 int64_t clp_shard_blob_bytes(void);
-/* solve() on a sharded handle: every rank calls it collectively with the same u0 (device
- * pointer); one persistent kernel per GPU, partial products exchanged through peer memory. */
-int clp_shard_solve(clp_handle h, const double* u0_dev, clp_solution* out, double* u_out_dev,
-                    int32_t* nodes_out);
+int clp_shard_export(clp_handle h, void* blob, int64_t blob_bytes, int64_t* written);
+/* blobs: world blobs in rank order, blob_bytes_each apart (CUDA IPC between processes, plain
+ * peer access when the exporting handle lives in the calling process). */
+int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, int world);
+/* CTAs of the persistent solver per SM (1 or 2, default 2). 1 lets two shards share one GPU,
+ * which is how the sharded path is exercised on a single-GPU box. */
+int clp_set_ctas_per_sm(clp_handle h, int n);
 
 #ifdef __cplusplus
 }
