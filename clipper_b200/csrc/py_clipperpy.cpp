@@ -234,7 +234,7 @@ PYBIND11_MODULE(clipperpy, m)
       const bool parallelize = (std::dynamic_pointer_cast<PyPairwiseInvariant>(invariant)) ? false : true;
       c->setParallelize(parallelize);
       return c;
-    }))
+    }), py::keep_alive<1, 2>())  // a Python-subclassed invariant must outlive the temporary it was passed as
     .def("__repr__", [](const clipper::CLIPPER&) { return std::string("<CLIPPER>"); })
     .def("score_pairwise_consistency",
          [](clipper::CLIPPER& c, const py::array& D1, const py::array& D2, const py::array& A) {
