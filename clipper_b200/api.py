@@ -295,6 +295,16 @@ class CLIPPER:
     def set_stream(self, cuda_stream):
         _capi.check(self._h, self._lib.clp_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def set_dense_mode(self, mode):
+        """2 (default): upper triangle read once, two-sided update; 1: stripes, full matrix; 0: segments"""
+        _capi.check(self._h, self._lib.clp_set_dense_mode(self._h, int(mode)))
+
+    def dense_mode(self):
+        """effective sweep mode of the current problem (sharded handles fall back from 2 to 1)"""
+        a, b = C.c_int(), C.c_int()
+        _capi.check(self._h, self._lib.clp_get_dense_mode(self._h, C.byref(a), C.byref(b)))
+        return int(b.value)
+
     def _sync_params(self):
         _capi.check(self._h, self._lib.clp_set_params(self._h, C.byref(self._params._pod())))
 

@@ -92,6 +92,12 @@ struct clp_handle_s {
   size_t pinned_cap = 0;
   Plan plan{};
   long long mpad = 0;
+  // stripe decomposition (clp_dense2.cuh)
+  int dense_mode = 2;     // requested: 0 segments, 1 stripes/full, 2 stripes/upper-triangle two-sided
+  int dense_mode_eff = 2; // effective (sharded handles cannot use 2)
+  Plan2 plan2{};
+  Dense2Buffers d2{};
+  DevBuf d2buf, plan2buf;
 
   size_t esize() const { return storage == CLP_STORE_F64 ? 8 : 4; }
 };
@@ -148,6 +154,82 @@ Plan make_plan(long long m, int rows_pad, int G) {
   return p;
 }
 
+
+// stripe decomposition: item enumeration, per-CTA runs, buffers (clp_dense2.cuh)
+int build_plan2(clp_handle h) {
+  const int G = h->sm_count * h->ctas_per_sm;
+  h->dense_mode_eff = (h->dense_mode == 2 && h->world > 1) ? 1 : h->dense_mode;
+  Plan2& p = h->plan2;
+  p.G = G;
+  p.sym = h->dense_mode_eff == 2 ? 1 : 0;
+  p.NST = (int)((h->m + kStripe - 1) / kStripe);
+  p.NRT = h->rows_pad / kRowTile;
+  std::vector<long long> prefix((size_t)p.NST + 1, 0);
+  for (int J = 0; J < p.NST; ++J) {
+    const long long nt = p.sym ? std::min<long long>(p.NRT, (long long)(J + 1) * (kStripe / kRowTile)) : p.NRT;
+    prefix[(size_t)J + 1] = prefix[(size_t)J] + nt;
+  }
+  p.T = prefix[(size_t)p.NST];
+  std::vector<int> first((size_t)G, 0), lo((size_t)p.NST, G), hi((size_t)p.NST, -1), has((size_t)G, 0);
+  int kmax = 1;
+  for (int b = 0; b < G; ++b) {
+    const long long t0 = p.T * b / G, t1 = p.T * (b + 1) / G;
+    if (t0 >= t1) continue;
+    has[(size_t)b] = 1;
+    int J = 0;
+    while (prefix[(size_t)J + 1] <= t0) ++J;
+    first[(size_t)b] = J;
+    int k = 0;
+    long long t = t0;
+    while (t < t1) {
+      lo[(size_t)J] = std::min(lo[(size_t)J], b); hi[(size_t)J] = std::max(hi[(size_t)J], b);
+      t = std::min(t1, prefix[(size_t)J + 1]); ++J; ++k;
+    }
+    kmax = std::max(kmax, k);
+  }
+  p.KMAX = kmax;
+  // symmetric mode: per stripe, the ordered list of column-partial slots (one per CTA run crossing the stripe)
+  std::vector<int> slot_begin((size_t)p.NST + 1, 0), slot_list;
+  for (int J = 0; J < p.NST; ++J) {
+    slot_begin[(size_t)J] = (int)slot_list.size();
+    if (p.sym)
+      for (int b = lo[(size_t)J]; b <= hi[(size_t)J]; ++b)
+        if (has[(size_t)b]) slot_list.push_back(b * kmax + (J - first[(size_t)b]));
+  }
+  slot_begin[(size_t)p.NST] = (int)slot_list.size();
+  // device copies of the small integer tables
+  const size_t b_prefix = ((size_t)p.NST + 1) * sizeof(long long);
+  const size_t b_int = (2 * (size_t)G + 2 * (size_t)p.NST + slot_begin.size() + slot_list.size()) * sizeof(int);
+  CLP_CUDA(h, h->plan2buf.ensure(b_prefix + b_int + 64));
+  char* base = h->plan2buf.as<char>();
+  std::vector<int> ints;
+  ints.insert(ints.end(), first.begin(), first.end());
+  ints.insert(ints.end(), lo.begin(), lo.end());
+  ints.insert(ints.end(), hi.begin(), hi.end());
+  ints.insert(ints.end(), has.begin(), has.end());
+  ints.insert(ints.end(), slot_begin.begin(), slot_begin.end());
+  ints.insert(ints.end(), slot_list.begin(), slot_list.end());
+  CLP_CUDA(h, cudaMemcpyAsync(base, prefix.data(), b_prefix, cudaMemcpyHostToDevice, h->stream));
+  CLP_CUDA(h, cudaMemcpyAsync(base + b_prefix, ints.data(), b_int, cudaMemcpyHostToDevice, h->stream));
+  CLP_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+  p.tile_prefix = reinterpret_cast<const long long*>(base);
+  p.cta_first_stripe = reinterpret_cast<const int*>(base + b_prefix);
+  p.stripe_cta_lo = p.cta_first_stripe + G;
+  p.stripe_cta_hi = p.stripe_cta_lo + p.NST;
+  p.cta_has_items = p.stripe_cta_hi + p.NST;
+  p.slot_begin = p.cta_has_items + G;
+  p.slot_list = p.slot_begin + p.NST + 1;
+  // partial-product buffers
+  const size_t n_row = (size_t)p.NST * h->rows_pad;
+  const size_t n_col = p.sym ? (size_t)G * p.KMAX * kStripe : 0;
+  CLP_CUDA(h, h->d2buf.ensure((2 * n_row + 2 * n_col + (size_t)G) * sizeof(double) + 64));
+  double* d = h->d2buf.as<double>();
+  h->d2.rowM = d; h->d2.rowC = d + n_row;
+  h->d2.colM = d + 2 * n_row; h->d2.colC = h->d2.colM + n_col;
+  h->d2.sumpart = h->d2.colC + n_col;
+  return CLP_OK;
+}
+
 // (re)allocate the matrix store for problem size m under the current shard config
 int ensure_matrix(clp_handle h, long long m) {
   if (m <= 0) return fail(h, CLP_ERR_INVALID, "number of associations must be positive");
@@ -160,6 +242,7 @@ int ensure_matrix(clp_handle h, long long m) {
   h->mpad = round_up(m, 128);
   CLP_CUDA(h, h->Mbuf.ensure((size_t)h->rows_pad * (size_t)h->ld * h->esize()));
   h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_per_sm);
+  if (int rc = build_plan2(h)) return rc;
   // workspace
   CLP_CUDA(h, h->vecs.ensure((size_t)V_SLOTS * h->mpad * sizeof(double)));
   {
@@ -274,13 +357,20 @@ int score_from_device(clp_handle h, int kind, const double* D1d, int d, long lon
 
 template <typename T>
 int launch_matvec(clp_handle h, const StageArgs& st, const double* v, double d, double* y, double* Mv, double* Cv) {
-  const Plan& p = h->plan;
-  double* partM = h->parts.as<double>();
-  double* partC = partM + (size_t)p.NSEG * h->rows_pad;
-  matvec_partials_kernel<T><<<p.G, kThreads, 0, h->stream>>>(mat_view(h), p, st, partM, partC);
-  CLP_CUDA(h, cudaGetLastError());
-  matvec_combine_kernel<<<(unsigned)((h->rows + 255) / 256), 256, 0, h->stream>>>(
-      mat_view(h), p, partM, partC, h->small.as<double>(), v, d, y, Mv, Cv);
+  const unsigned cb = (unsigned)((h->rows + 255) / 256);
+  if (h->dense_mode_eff == 0) {
+    const Plan& p = h->plan;
+    double* partM = h->parts.as<double>();
+    double* partC = partM + (size_t)p.NSEG * h->rows_pad;
+    matvec_partials_kernel<T><<<p.G, kThreads, 0, h->stream>>>(mat_view(h), p, st, partM, partC);
+    CLP_CUDA(h, cudaGetLastError());
+    matvec_combine_kernel<<<cb, 256, 0, h->stream>>>(mat_view(h), p, partM, partC, h->small.as<double>(), v, d, y, Mv, Cv);
+  } else {
+    if (h->dense_mode_eff == 2) matvec2_partials_kernel<T, true><<<h->plan2.G, kThreads, 0, h->stream>>>(mat_view(h), h->plan2, st, h->d2);
+    else matvec2_partials_kernel<T, false><<<h->plan2.G, kThreads, 0, h->stream>>>(mat_view(h), h->plan2, st, h->d2);
+    CLP_CUDA(h, cudaGetLastError());
+    matvec2_combine_kernel<<<cb, 256, 0, h->stream>>>(mat_view(h), h->plan2, h->d2, v, d, y, Mv, Cv);
+  }
   CLP_CUDA(h, cudaGetLastError());
   return CLP_OK;
 }
@@ -297,7 +387,9 @@ int matvec_enqueue(clp_handle h, const double* v_dev, double d, double* y_dev, d
 template <typename T>
 cudaError_t launch_solver(clp_handle h, SolverArgs& a) {
   void* args[] = {&a};
-  return cudaLaunchCooperativeKernel((const void*)solver_kernel<T>, dim3(h->plan.G), dim3(kThreads), args, 0, h->stream);
+  const void* fn = h->dense_mode_eff == 2 ? (const void*)solver_kernel<T, 2>
+                 : h->dense_mode_eff == 1 ? (const void*)solver_kernel<T, 1> : (const void*)solver_kernel<T, 0>;
+  return cudaLaunchCooperativeKernel(fn, dim3(h->plan.G), dim3(kThreads), args, 0, h->stream);
 }
 
 struct ResultHeader {  // first 256 bytes of the result buffer
@@ -325,6 +417,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   a.partC = a.partM + (size_t)h->plan.NSEG * h->rows_pad;
   a.segsum = h->small.as<double>();
   a.red = h->small.as<double>() + kMaxSeg;
+  a.plan2 = h->plan2; a.d2 = h->d2;
   a.out = reinterpret_cast<SolverOut*>(h->result.p);
   a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
   a.rank = h->rank; a.world = h->world; a.seq0 = h->seq;
@@ -455,8 +548,19 @@ int clp_create(int device, int storage, clp_handle* out) {
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = h->sync.ensure(sizeof(SyncBlock))) != cudaSuccess) return bail("cudaMalloc", e);
   int occ = 0;
-  if (storage == CLP_STORE_F64) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solver_kernel<double>, kThreads, 0);
-  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solver_kernel<float>, kThreads, 0);
+  {
+    int o0 = 0, o1 = 0, o2 = 0;
+    if (storage == CLP_STORE_F64) {
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, solver_kernel<double, 0>, kThreads, 0);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, solver_kernel<double, 1>, kThreads, 0);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, solver_kernel<double, 2>, kThreads, 0);
+    } else {
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, solver_kernel<float, 0>, kThreads, 0);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, solver_kernel<float, 1>, kThreads, 0);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, solver_kernel<float, 2>, kThreads, 0);
+    }
+    occ = std::min(o0, std::min(o1, o2));
+  }
   if (e != cudaSuccess || occ < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
   h->ctas_per_sm = std::min(occ, 2);
   *out = h;
@@ -469,7 +573,7 @@ int clp_destroy(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r)
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
-  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->parts, &h->small,
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->parts, &h->small,
                     &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -820,7 +924,29 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
 int clp_set_ctas_per_sm(clp_handle h, int n) {
   if (!h || n < 1 || n > 2) return fail(h, CLP_ERR_INVALID, "ctas_per_sm must be 1 or 2");
   h->ctas_per_sm = n;
-  if (h->m > 0) h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_per_sm);
+  if (h->m > 0) {
+    h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_per_sm);
+    CLP_CUDA(h, cudaSetDevice(h->device));
+    CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
+    if (int rc = build_plan2(h)) return rc;
+  }
+  return CLP_OK;
+}
+
+int clp_get_dense_mode(clp_handle h, int* requested, int* effective) {
+  if (!h) return CLP_ERR_INVALID;
+  if (requested) *requested = h->dense_mode;
+  if (effective) *effective = h->dense_mode_eff;
+  return CLP_OK;
+}
+
+int clp_set_dense_mode(clp_handle h, int mode) {
+  if (!h || mode < 0 || mode > 2) return fail(h, CLP_ERR_INVALID, "dense mode must be 0, 1 or 2");
+  h->dense_mode = mode;
+  if (h->m > 0) {
+    CLP_CUDA(h, cudaSetDevice(h->device));
+    if (int rc = build_plan2(h)) return rc;
+  }
   return CLP_OK;
 }
 

@@ -544,6 +544,10 @@ __device__ __forceinline__ double grad_entry(double ui, double sumu, double Mv, 
   return __dadd_rn(__dadd_rn(__dsub_rn(t1, t2), Mv), __dmul_rn(Cv, d));
 }
 
+}  // namespace clp
+#include "clp_dense2.cuh"
+namespace clp {
+
 // ------------------------------------------------------------------------------------------
 // stand-alone mat-vec kernels (clp_matvec / the c5 sweep): partials, then combine
 // ------------------------------------------------------------------------------------------
@@ -564,6 +568,28 @@ __global__ void matvec_combine_kernel(MatView mv, Plan p, const double* partM, c
   for (int s = 0; s < p.NSEG; ++s) sumv += segsum[s];
   double Mv, Cv;
   gather_partials(partM, partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
+  const int i = mv.row0 + lr;
+  if (Mv_out) Mv_out[i] = Mv;
+  if (Cv_out) Cv_out[i] = Cv;
+  if (y) y[i] = grad_entry(v[i], sumv, Mv, Cv, d);
+}
+
+// the same two steps for the stripe decomposition (clp_dense2.cuh)
+template <typename T, bool SYM>
+__global__ void __launch_bounds__(kThreads, 2)
+matvec2_partials_kernel(MatView mv, Plan2 p, StageArgs st, Dense2Buffers buf) {
+  __shared__ __align__(16) double smem[2 * 8 * 32 * 2 + 2 * 32];
+  dense2_phase<T, SYM>(mv, p, st, buf, smem);
+}
+
+__global__ void matvec2_combine_kernel(MatView mv, Plan2 p, Dense2Buffers buf, const double* v, double d, double* y,
+                                       double* Mv_out, double* Cv_out) {
+  __shared__ double smem[kWarps];
+  const double sumv = block_sum_ordered(buf.sumpart, p.G, smem);
+  const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lr >= mv.rows) return;
+  double Mv, Cv;
+  dense2_gather(mv, p, buf, lr, Mv, Cv);
   const int i = mv.row0 + lr;
   if (Mv_out) Mv_out[i] = Mv;
   if (Cv_out) Cv_out[i] = Cv;
@@ -617,6 +643,8 @@ struct SolverArgs {
   double* partC;
   double* segsum;    // [NSEG]
   double* red;       // [2][G][kRedVals]  per-CTA partial sums, double-buffered
+  Plan2 plan2;       // stripe decomposition (MODE 1, 2)
+  Dense2Buffers d2;
   double* u_final;   // [m] copy of the final iterate
   SolverOut* out;
   // row-block sharding
@@ -739,7 +767,9 @@ __device__ bool exchange_sums(const SolverArgs& a, const double (&loc)[kRedVals]
   return *reinterpret_cast<volatile int*>(&sb->error) == 0;
 }
 
-template <typename T>
+// MODE 0: column-segment decomposition (matvec_phase); 1: stripes, full matrix; 2: stripes, upper triangle
+// read once and applied two-sidedly (single GPU)
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   __shared__ __align__(16) double vs[kSegMax];
   __shared__ double red_smem[kWarps * kRedVals + kMaxPeers * kRedVals];
@@ -751,14 +781,18 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   const int gthreads = p.G * kThreads;
   double vals[kRedVals];
   double loc[kRedVals];
-  double* const U[2] = {a.vecs + (size_t)V_U0 * a.mpad, a.vecs + (size_t)V_U1 * a.mpad};
-  double* const MV[2] = {a.vecs + (size_t)V_MV0 * a.mpad, a.vecs + (size_t)V_MV1 * a.mpad};
-  double* const CV[2] = {a.vecs + (size_t)V_CV0 * a.mpad, a.vecs + (size_t)V_CV1 * a.mpad};
-  const uint4* const GL[2] = {a.ll + (size_t)L_G0 * a.mpad, a.ll + (size_t)L_G1 * a.mpad};
+  struct Vecs {  // U[c], MV[c], CV[c], GL[c] by arithmetic (no dynamically indexed local arrays)
+    double* v; const uint4* l; long long mp;
+    __device__ __forceinline__ double* U(int c) const { return v + (size_t)(V_U0 + c) * mp; }
+    __device__ __forceinline__ double* MV(int c) const { return v + (size_t)(V_MV0 + c) * mp; }
+    __device__ __forceinline__ double* CV(int c) const { return v + (size_t)(V_CV0 + c) * mp; }
+    __device__ __forceinline__ const uint4* GL(int c) const { return l + (size_t)(L_G0 + c) * mp; }
+  };
+  const Vecs X{a.vecs, a.ll, a.mpad};
   int* const errp = &a.bar.sb->error;
 
   long long n_evals = 0, n_inner = 0, n_matvec = 0;
-  int cur = 0;  // U[cur], G[cur], MV[cur], CV[cur] describe the current iterate
+  int cur = 0;  // X.U(cur), G[cur], X.MV(cur), X.CV(cur) describe the current iterate
   double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0;
   int i_outer = 0;
   int status = 0;
@@ -767,12 +801,26 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   int red_par = 0;
   unsigned long long round = 0;     // barrier rounds of this launch
   unsigned long long seq = a.seq0;  // exchange steps since the shards were connected (LL tags)
-  unsigned tagG[2] = {0u, 0u};      // tag under which G[0] / G[1] were last written
+  unsigned tagG0 = 0u, tagG1 = 0u;  // tag under which G[0] / G[1] were last written
   unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, tmark = global_ns();
 #define CLP_LAP(acc) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; }
 
 #define CLP_ZERO_LOC()            \
   _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
+  // rows are dealt to the CTAs in chunks of 32 consecutive rows, round-robin (chunk c -> CTA c % G):
+  // coalesced inside a warp, and every CTA gets rows from all parts of the matrix (the gather cost of a
+  // row grows with its stripe index in the symmetric mode)
+#define CLP_FOR_ROWS(lr)                                                                    \
+  for (int lr = (blockIdx.x + p.G * (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31); lr < mv.rows; lr += p.G * kWarps * 32)
+#define CLP_DENSE_PASS()                                                                    \
+  if constexpr (MODE == 0) matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem);      \
+  else dense2_phase<T, MODE == 2>(mv, a.plan2, st, a.d2, vs);
+#define CLP_GATHER()                                                                        \
+  if constexpr (MODE == 0) gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv); \
+  else dense2_gather(mv, a.plan2, a.d2, lr, Mv, Cv);
+#define CLP_SUMV(out)                                                                       \
+  if constexpr (MODE == 0) { out = 0.0; for (int s_ = 0; s_ < p.NSEG; ++s_) out += __ldcg(a.segsum + s_); } \
+  else out = block_sum_ordered(a.d2.sumpart, a.plan2.G, red_smem);
 #define CLP_EXCHANGE()                                                                      \
   CLP_LAP(ns_cb);                                                                           \
   if (!exchange_sums(a, loc, vals, red_par, round, seq, red_smem, &smem_flag)) { status = 5; goto finish; } \
@@ -789,17 +837,17 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
     st.llA = nullptr; st.llB = nullptr; st.tag = 0; st.error = errp; st.alpha = 0.0; st.segsum = a.segsum;
     if (P.rescale_u0) {
       st.mode = STAGE_RAW; st.srcA = a.u0; st.z = 1.0; st.dst = nullptr;
-      matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec;
+      CLP_DENSE_PASS(); ++n_matvec;
       CLP_BAR_CHECK();
     }
     CLP_ZERO_LOC();
     const unsigned tagX = (unsigned)(seq + 1);
-    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+    CLP_FOR_ROWS(lr) {
       const int i = mv.row0 + lr;
       double t = a.u0[i];
       if (P.rescale_u0) {
         double Mv, Cv;
-        gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
+        CLP_GATHER();
         t = __dadd_rn(Mv, t);  // M*u0 + u0
       }
       store_replicated(a, L_X, i, t, tagX);
@@ -808,24 +856,24 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
     CLP_EXCHANGE();
     // u /= u.norm(), then Mhat u, Chat u for the initial d
     st.mode = STAGE_DIV; st.srcA = nullptr; st.llA = a.ll + (size_t)L_X * a.mpad; st.tag = tagX;
-    st.z = vals[0]; st.dst = U[1];
-    matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec;
+    st.z = vals[0]; st.dst = X.U(1);
+    CLP_DENSE_PASS(); ++n_matvec;
     cur = 1;
     CLP_BAR_CHECK();
   }
 
   // ---- combine for the initial iterate + initial d (clipper.cpp:201-209) ------------------
   {
-    double sumu = 0.0;
-    for (int s = 0; s < p.NSEG; ++s) sumu += __ldcg(a.segsum + s);
+    double sumu;
+    CLP_SUMV(sumu);
     sum_cur = sumu;
     CLP_ZERO_LOC();
-    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+    CLP_FOR_ROWS(lr) {
       const int i = mv.row0 + lr;
       double Mv, Cv;
-      gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
-      MV[cur][i] = Mv; CV[cur][i] = Cv;
-      const double ui = U[cur][i];
+      CLP_GATHER();
+      X.MV(cur)[i] = Mv; X.CV(cur)[i] = Cv;
+      const double ui = X.U(cur)[i];
       const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sumu), Cv), ui);
       if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += __dadd_rn(Mv, ui) / cbu; }
     }
@@ -838,12 +886,12 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
     // gradF and F for the current u under the current d (clipper.cpp:219-220), plus the squared
     // norm of the first trial point max(u + gradF, 0)
     CLP_ZERO_LOC();
-    tagG[cur] = (unsigned)(seq + 1);
-    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+    { const unsigned t_ = (unsigned)(seq + 1); if (cur) tagG1 = t_; else tagG0 = t_; }
+    CLP_FOR_ROWS(lr) {
       const int i = mv.row0 + lr;
-      const double ui = U[cur][i];
-      const double g = grad_entry(ui, sum_cur, MV[cur][i], CV[cur][i], d);
-      store_replicated(a, L_G0 + cur, i, g, tagG[cur]);
+      const double ui = X.U(cur)[i];
+      const double g = grad_entry(ui, sum_cur, X.MV(cur)[i], X.CV(cur)[i], d);
+      store_replicated(a, L_G0 + cur, i, g, (cur ? tagG1 : tagG0));
       loc[0] += ui * g;
       double w = __dadd_rn(ui, __dmul_rn(1.0, g)); w = (w < 0.0) ? 0.0 : w;
       loc[1] += w * w;
@@ -859,25 +907,25 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
       for (int k = 0; k < P.maxlsiters; ++k) {
         // Phase A: candidate point + dense pass over the local rows of M
         StageArgs st;
-        st.mode = STAGE_STEP; st.srcA = U[cur]; st.llA = nullptr; st.llB = GL[cur]; st.tag = tagG[cur];
-        st.error = errp; st.alpha = alpha; st.z = z; st.dst = U[nxt]; st.segsum = a.segsum;
-        matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem); ++n_matvec; ++n_evals;
+        st.mode = STAGE_STEP; st.srcA = X.U(cur); st.llA = nullptr; st.llB = X.GL(cur); st.tag = (cur ? tagG1 : tagG0);
+        st.error = errp; st.alpha = alpha; st.z = z; st.dst = X.U(nxt); st.segsum = a.segsum;
+        CLP_DENSE_PASS(); ++n_matvec; ++n_evals;
         CLP_BAR_CHECK();
         // Phase B: gradFnew, Fnew, |unew-u|^2 and the squared norms of both possible next trials
-        double sumv = 0.0;
-        for (int s = 0; s < p.NSEG; ++s) sumv += __ldcg(a.segsum + s);
+        double sumv;
+        CLP_SUMV(sumv);
         const double alpha_rej = __dmul_rn(alpha, P.beta);
         CLP_ZERO_LOC();
-        tagG[nxt] = (unsigned)(seq + 1);
-        for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+        { const unsigned t_ = (unsigned)(seq + 1); if (nxt) tagG1 = t_; else tagG0 = t_; }
+        CLP_FOR_ROWS(lr) {
           const int i = mv.row0 + lr;
           double Mv, Cv;
-          gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv);
-          MV[nxt][i] = Mv; CV[nxt][i] = Cv;
-          const double un = U[nxt][i];
+          CLP_GATHER();
+          X.MV(nxt)[i] = Mv; X.CV(nxt)[i] = Cv;
+          const double un = X.U(nxt)[i];
           const double g = grad_entry(un, sumv, Mv, Cv, d);
-          store_replicated(a, L_G0 + nxt, i, g, tagG[nxt]);
-          const double uo = U[cur][i], go = ll_load(GL[cur] + i, tagG[cur], errp);
+          store_replicated(a, L_G0 + nxt, i, g, (nxt ? tagG1 : tagG0));
+          const double uo = X.U(cur)[i], go = ll_load(X.GL(cur) + i, (cur ? tagG1 : tagG0), errp);
           loc[0] += un * g;
           const double du = __dsub_rn(un, uo);
           loc[1] += du * du;
@@ -909,11 +957,11 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
 
     // penalty ramp (clipper.cpp:268-280); MV/CV/sum_cur belong to the accepted u
     CLP_ZERO_LOC();
-    for (int lr = gtid; lr < mv.rows; lr += gthreads) {
+    CLP_FOR_ROWS(lr) {
       const int i = mv.row0 + lr;
-      const double ui = U[cur][i];
-      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), CV[cur][i]), ui);
-      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(MV[cur][i], ui) / cbu); }
+      const double ui = X.U(cur)[i];
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), X.CV(cur)[i]), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(X.MV(cur)[i], ui) / cbu); }
     }
     CLP_EXCHANGE();
     if (vals[0] > 0.0) d += vals[1] / vals[0];
@@ -922,7 +970,7 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
 
   // every rank holds the complete iterate; copy it out, then (multi-GPU) one last rendez-vous so
   // that no rank starts overwriting a peer's replicas while that peer is still inside this launch
-  for (int i = gtid; i < mv.m; i += gthreads) a.u_final[i] = U[cur][i];
+  for (int i = gtid; i < mv.m; i += gthreads) a.u_final[i] = X.U(cur)[i];
   if (a.world > 1) {
     CLP_ZERO_LOC();
     CLP_EXCHANGE();
@@ -935,6 +983,10 @@ finish:
     a.out->ns_matvec = ns_mv; a.out->ns_combine = ns_cb; a.out->ns_exchange = ns_ex;
   }
 #undef CLP_LAP
+#undef CLP_FOR_ROWS
+#undef CLP_DENSE_PASS
+#undef CLP_GATHER
+#undef CLP_SUMV
 #undef CLP_ZERO_LOC
 #undef CLP_EXCHANGE
 #undef CLP_BAR_CHECK

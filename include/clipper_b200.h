@@ -176,6 +176,13 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
 /* CTAs of the persistent solver per SM (1 or 2, default 2). 1 lets two shards share one GPU,
  * which is how the sharded path is exercised on a single-GPU box. */
 int clp_set_ctas_per_sm(clp_handle h, int n);
+/* How the solver / mat-vec sweep the dense matrix:
+ *   2 (default on unsharded handles): column stripes, ONLY the upper triangle is read and every element
+ *     is applied two-sidedly in-tile -> ~2 m^2 bytes per objective evaluation (fp32 storage);
+ *   1: column stripes, full matrix (4 m^2 bytes; what sharded handles use);
+ *   0: first-generation column-segment decomposition, full matrix. */
+int clp_set_dense_mode(clp_handle h, int mode);
+int clp_get_dense_mode(clp_handle h, int* requested, int* effective);
 
 #ifdef __cplusplus
 }
