@@ -296,7 +296,7 @@ class CLIPPER:
         _capi.check(self._h, self._lib.clp_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def set_dense_mode(self, mode):
-        """2 (default): upper triangle read once, two-sided update; 1: stripes, full matrix; 0: segments"""
+        """4 (default) auto; 3 compact rows; 2 upper triangle read once, two-sided update; 1 stripes/full; 0 segments"""
         _capi.check(self._h, self._lib.clp_set_dense_mode(self._h, int(mode)))
 
     def dense_mode(self):
@@ -304,6 +304,12 @@ class CLIPPER:
         a, b = C.c_int(), C.c_int()
         _capi.check(self._h, self._lib.clp_get_dense_mode(self._h, C.byref(a), C.byref(b)))
         return int(b.value)
+
+    def sparse_info(self):
+        """(entries kept by the compact-row copy, algorithmic bytes of one sparse pass)"""
+        a, b = C.c_int64(), C.c_int64()
+        _capi.check(self._h, self._lib.clp_sparse_info(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def _sync_params(self):
         _capi.check(self._h, self._lib.clp_set_params(self._h, C.byref(self._params._pod())))

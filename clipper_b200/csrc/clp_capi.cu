@@ -93,8 +93,13 @@ struct clp_handle_s {
   Plan plan{};
   long long mpad = 0;
   // stripe decomposition (clp_dense2.cuh)
-  int dense_mode = 2;     // requested: 0 segments, 1 stripes/full, 2 stripes/upper-triangle two-sided
-  int dense_mode_eff = 2; // effective (sharded handles cannot use 2)
+  int dense_mode = 4;     // requested: 0 segments, 1 stripes/full, 2 stripes/upper-triangle two-sided,
+                          //            3 compact rows, 4 auto (compact rows when the graph is sparse enough, else 2 / 0)
+  int dense_mode_eff = 2; // effective, decided when the matrix is finalised
+  // compact-row copy (clp_sparse.cuh)
+  DevBuf sp_val, sp_col, sp_rowptr, sp_segoff, sp_rowcnt;
+  unsigned long long sp_nnz = 0, sp_nnz_real = 0;
+  SparseView sp{};
   Plan2 plan2{};
   Dense2Buffers d2{};
   DevBuf d2buf, plan2buf;
@@ -118,6 +123,7 @@ int fail(clp_handle h, int code, const std::string& msg) {
   } while (0)
 
 inline long long round_up(long long x, long long q) { return (x + q - 1) / q * q; }
+int reset_sync(clp_handle h);
 
 int ensure_pinned(clp_handle h, size_t bytes) {
   if (bytes <= h->pinned_cap) return CLP_OK;
@@ -158,7 +164,6 @@ Plan make_plan(long long m, int rows_pad, int G) {
 // stripe decomposition: item enumeration, per-CTA runs, buffers (clp_dense2.cuh)
 int build_plan2(clp_handle h) {
   const int G = h->sm_count * h->ctas_per_sm;
-  h->dense_mode_eff = (h->dense_mode == 2 && h->world > 1) ? 1 : h->dense_mode;
   Plan2& p = h->plan2;
   p.G = G;
   p.sym = h->dense_mode_eff == 2 ? 1 : 0;
@@ -230,6 +235,61 @@ int build_plan2(clp_handle h) {
   return CLP_OK;
 }
 
+
+// Called once the dense store holds the new matrix: pick the sweep (dense mode) and build what it needs.
+template <typename T>
+int build_sparse(clp_handle h, bool force) {
+  const Plan& p = h->plan;
+  const int nseg = p.NSEG;
+  CLP_CUDA(h, h->sp_segoff.ensure((size_t)h->rows_pad * (nseg + 1) * sizeof(unsigned int)));
+  CLP_CUDA(h, h->sp_rowcnt.ensure((size_t)h->rows_pad * sizeof(unsigned long long)));
+  CLP_CUDA(h, h->sp_rowptr.ensure(((size_t)h->rows_pad + 1) * sizeof(unsigned long long)));
+  const T* M = h->Mbuf.as<T>();
+  const unsigned blocks = (unsigned)(((size_t)h->rows_pad * 32 + 255) / 256);
+  if (int rc = reset_sync(h)) return rc;
+  SyncBlock* sb = h->sync.as<SyncBlock>();
+  sparse_count_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
+                                                        h->sp_segoff.as<unsigned int>(), h->sp_rowcnt.as<unsigned long long>(),
+                                                        &sb->counts[0]);
+  CLP_CUDA(h, cudaGetLastError());
+  sparse_scan_kernel<<<1, 1024, 0, h->stream>>>(h->sp_rowcnt.as<unsigned long long>(), h->rows_pad,
+                                                 h->sp_rowptr.as<unsigned long long>());
+  CLP_CUDA(h, cudaGetLastError());
+  unsigned long long nnz = 0, nreal = 0;
+  CLP_CUDA(h, cudaMemcpyAsync(&nnz, h->sp_rowptr.as<unsigned long long>() + h->rows_pad, sizeof(nnz), cudaMemcpyDeviceToHost, h->stream));
+  CLP_CUDA(h, cudaMemcpyAsync(&nreal, &sb->counts[0], sizeof(nreal), cudaMemcpyDeviceToHost, h->stream));
+  CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->sp_nnz = nnz;        // stored entries (slices padded to multiples of 4): what one pass reads
+  h->sp_nnz_real = nreal; // non-neutral entries of the local rows
+  // worth it?  compare with the bytes of the best dense sweep (upper triangle two-sided on one GPU, full rows when sharded)
+  const double sparse_bytes = (double)nnz * (sizeof(T) + 2.0);
+  const double dense_bytes = (h->world > 1) ? (double)sizeof(T) * h->rows * (double)h->m : 0.5 * sizeof(T) * (double)h->m * (double)h->m;
+  if (!force && !(sparse_bytes < 0.8 * dense_bytes)) return 1;  // keep a dense sweep
+  CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(nnz, 1) * sizeof(T)));
+  CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(nnz, 1) * sizeof(unsigned short)));
+  sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, p.W, nseg, h->sp_rowptr.as<unsigned long long>(),
+                                                       h->sp_segoff.as<unsigned int>(), h->sp_val.as<T>(), h->sp_col.as<unsigned short>());
+  CLP_CUDA(h, cudaGetLastError());
+  h->sp.val = h->sp_val.p; h->sp.col16 = h->sp_col.as<unsigned short>();
+  h->sp.row_ptr = h->sp_rowptr.as<unsigned long long>(); h->sp.seg_off = h->sp_segoff.as<unsigned int>();
+  h->sp.nseg = nseg;
+  return CLP_OK;
+}
+
+int finalize_matrix(clp_handle h) {
+  int eff = h->dense_mode;
+  if (eff == 3 || eff == 4) {
+    const int rc = (h->storage == CLP_STORE_F64) ? build_sparse<double>(h, eff == 3) : build_sparse<float>(h, eff == 3);
+    if (rc == CLP_OK) eff = 3;
+    else if (rc == 1) eff = (h->world > 1) ? 0 : 2;
+    else return rc;
+  }
+  if (eff == 2 && h->world > 1) eff = 1;
+  h->dense_mode_eff = eff;
+  if (eff == 1 || eff == 2) { if (int rc = build_plan2(h)) return rc; }
+  return CLP_OK;
+}
+
 // (re)allocate the matrix store for problem size m under the current shard config
 int ensure_matrix(clp_handle h, long long m) {
   if (m <= 0) return fail(h, CLP_ERR_INVALID, "number of associations must be positive");
@@ -242,7 +302,6 @@ int ensure_matrix(clp_handle h, long long m) {
   h->mpad = round_up(m, 128);
   CLP_CUDA(h, h->Mbuf.ensure((size_t)h->rows_pad * (size_t)h->ld * h->esize()));
   h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_per_sm);
-  if (int rc = build_plan2(h)) return rc;
   // workspace
   CLP_CUDA(h, h->vecs.ensure((size_t)V_SLOTS * h->mpad * sizeof(double)));
   {
@@ -313,6 +372,7 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   SyncBlock host;
   if ((rc = read_sync(h, &host))) return rc;
   if (host.error == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
+  if ((rc = finalize_matrix(h))) return rc;
   h->has_matrix = true;
   h->has_A = true;
   return CLP_OK;
@@ -358,11 +418,12 @@ int score_from_device(clp_handle h, int kind, const double* D1d, int d, long lon
 template <typename T>
 int launch_matvec(clp_handle h, const StageArgs& st, const double* v, double d, double* y, double* Mv, double* Cv) {
   const unsigned cb = (unsigned)((h->rows + 255) / 256);
-  if (h->dense_mode_eff == 0) {
+  if (h->dense_mode_eff == 0 || h->dense_mode_eff == 3) {
     const Plan& p = h->plan;
     double* partM = h->parts.as<double>();
     double* partC = partM + (size_t)p.NSEG * h->rows_pad;
-    matvec_partials_kernel<T><<<p.G, kThreads, 0, h->stream>>>(mat_view(h), p, st, partM, partC);
+    if (h->dense_mode_eff == 3) matvec_sparse_partials_kernel<T><<<p.G, kThreads, 0, h->stream>>>(mat_view(h), p, st, h->sp, partM, partC);
+    else matvec_partials_kernel<T><<<p.G, kThreads, 0, h->stream>>>(mat_view(h), p, st, partM, partC);
     CLP_CUDA(h, cudaGetLastError());
     matvec_combine_kernel<<<cb, 256, 0, h->stream>>>(mat_view(h), p, partM, partC, h->small.as<double>(), v, d, y, Mv, Cv);
   } else {
@@ -387,7 +448,8 @@ int matvec_enqueue(clp_handle h, const double* v_dev, double d, double* y_dev, d
 template <typename T>
 cudaError_t launch_solver(clp_handle h, SolverArgs& a) {
   void* args[] = {&a};
-  const void* fn = h->dense_mode_eff == 2 ? (const void*)solver_kernel<T, 2>
+  const void* fn = h->dense_mode_eff == 3 ? (const void*)solver_kernel<T, 3>
+                 : h->dense_mode_eff == 2 ? (const void*)solver_kernel<T, 2>
                  : h->dense_mode_eff == 1 ? (const void*)solver_kernel<T, 1> : (const void*)solver_kernel<T, 0>;
   return cudaLaunchCooperativeKernel(fn, dim3(h->plan.G), dim3(kThreads), args, 0, h->stream);
 }
@@ -417,7 +479,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   a.partC = a.partM + (size_t)h->plan.NSEG * h->rows_pad;
   a.segsum = h->small.as<double>();
   a.red = h->small.as<double>() + kMaxSeg;
-  a.plan2 = h->plan2; a.d2 = h->d2;
+  a.plan2 = h->plan2; a.d2 = h->d2; a.sp = h->sp;
   a.out = reinterpret_cast<SolverOut*>(h->result.p);
   a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
   a.rank = h->rank; a.world = h->world; a.seq0 = h->seq;
@@ -554,10 +616,12 @@ int clp_create(int device, int storage, clp_handle* out) {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, solver_kernel<double, 0>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, solver_kernel<double, 1>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, solver_kernel<double, 2>, kThreads, 0);
+      if (e == cudaSuccess) { int o3 = 0; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, solver_kernel<double, 3>, kThreads, 0); o2 = std::min(o2, o3); }
     } else {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, solver_kernel<float, 0>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, solver_kernel<float, 1>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, solver_kernel<float, 2>, kThreads, 0);
+      if (e == cudaSuccess) { int o3 = 0; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, solver_kernel<float, 3>, kThreads, 0); o2 = std::min(o2, o3); }
     }
     occ = std::min(o0, std::min(o1, o2));
   }
@@ -573,7 +637,7 @@ int clp_destroy(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r)
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
-  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->parts, &h->small,
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_rowptr, &h->sp_segoff, &h->sp_rowcnt, &h->parts, &h->small,
                     &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -657,6 +721,7 @@ int clp_set_dense(clp_handle h, const double* M, const double* C, int64_t m) {
   if (int rc = read_sync(h, &host)) return rc;
   if (host.flags & 1) return fail(h, CLP_ERR_UNSUPPORTED, "affinity matrix has negative entries (contract: M in [0,1], ref clipper.h:166-171)");
   if (host.flags & 2) return fail(h, CLP_ERR_UNSUPPORTED, "constraint matrix is not binary (contract: ref clipper.h:176)");
+  if (int rc = finalize_matrix(h)) return rc;
   h->has_matrix = true;
   return CLP_OK;
 }
@@ -703,6 +768,7 @@ int clp_set_sparse_upper(clp_handle h, int64_t m, const int64_t* cpM, const int3
   if (host.flags & 4) return fail(h, CLP_ERR_INVALID, "sparse input is not strictly upper triangular (ref clipper.h:137-138)");
   if (host.flags & 1) return fail(h, CLP_ERR_UNSUPPORTED, "affinity matrix has negative entries");
   if (host.flags & 2) return fail(h, CLP_ERR_UNSUPPORTED, "constraint matrix is not binary");
+  if (int rc = finalize_matrix(h)) return rc;
   h->has_matrix = true;
   return CLP_OK;
 }
@@ -928,8 +994,17 @@ int clp_set_ctas_per_sm(clp_handle h, int n) {
     h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_per_sm);
     CLP_CUDA(h, cudaSetDevice(h->device));
     CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
-    if (int rc = build_plan2(h)) return rc;
+    CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
+    if (h->has_matrix) { if (int rc = finalize_matrix(h)) return rc; }
   }
+  return CLP_OK;
+}
+
+int clp_sparse_info(clp_handle h, int64_t* nnz_kept, int64_t* bytes_per_pass) {
+  if (!h) return CLP_ERR_INVALID;
+  if (nnz_kept) *nnz_kept = (int64_t)h->sp_nnz_real;
+  if (bytes_per_pass)
+    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) + (unsigned long long)h->rows * ((h->plan.NSEG + 1) * 4 + 8));
   return CLP_OK;
 }
 
@@ -941,11 +1016,11 @@ int clp_get_dense_mode(clp_handle h, int* requested, int* effective) {
 }
 
 int clp_set_dense_mode(clp_handle h, int mode) {
-  if (!h || mode < 0 || mode > 2) return fail(h, CLP_ERR_INVALID, "dense mode must be 0, 1 or 2");
+  if (!h || mode < 0 || mode > 4) return fail(h, CLP_ERR_INVALID, "sweep mode must be 0..4");
   h->dense_mode = mode;
-  if (h->m > 0) {
+  if (h->has_matrix) {
     CLP_CUDA(h, cudaSetDevice(h->device));
-    if (int rc = build_plan2(h)) return rc;
+    if (int rc = finalize_matrix(h)) return rc;
   }
   return CLP_OK;
 }

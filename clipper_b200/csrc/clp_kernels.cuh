@@ -546,6 +546,7 @@ __device__ __forceinline__ double grad_entry(double ui, double sumu, double Mv, 
 
 }  // namespace clp
 #include "clp_dense2.cuh"
+#include "clp_sparse.cuh"
 namespace clp {
 
 // ------------------------------------------------------------------------------------------
@@ -572,6 +573,15 @@ __global__ void matvec_combine_kernel(MatView mv, Plan p, const double* partM, c
   if (Mv_out) Mv_out[i] = Mv;
   if (Cv_out) Cv_out[i] = Cv;
   if (y) y[i] = grad_entry(v[i], sumv, Mv, Cv, d);
+}
+
+// sparse sweep (clp_sparse.cuh); the combine step is matvec_combine_kernel
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+matvec_sparse_partials_kernel(MatView mv, Plan p, StageArgs st, SparseView sp, double* partM, double* partC) {
+  __shared__ __align__(16) double vs[kSegMax];
+  __shared__ double red_smem[kWarps];
+  sparse_phase<T>(mv, p, st, sp, partM, partC, vs, red_smem);
 }
 
 // the same two steps for the stripe decomposition (clp_dense2.cuh)
@@ -645,6 +655,7 @@ struct SolverArgs {
   double* red;       // [2][G][kRedVals]  per-CTA partial sums, double-buffered
   Plan2 plan2;       // stripe decomposition (MODE 1, 2)
   Dense2Buffers d2;
+  SparseView sp;     // compact rows (MODE 3)
   double* u_final;   // [m] copy of the final iterate
   SolverOut* out;
   // row-block sharding
@@ -768,7 +779,7 @@ __device__ bool exchange_sums(const SolverArgs& a, const double (&loc)[kRedVals]
 }
 
 // MODE 0: column-segment decomposition (matvec_phase); 1: stripes, full matrix; 2: stripes, upper triangle
-// read once and applied two-sidedly (single GPU)
+// read once and applied two-sidedly (single GPU); 3: compact rows (clp_sparse.cuh) in the MODE-0 decomposition
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   __shared__ __align__(16) double vs[kSegMax];
@@ -814,12 +825,13 @@ __global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
   for (int lr = (blockIdx.x + p.G * (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31); lr < mv.rows; lr += p.G * kWarps * 32)
 #define CLP_DENSE_PASS()                                                                    \
   if constexpr (MODE == 0) matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem);      \
+  else if constexpr (MODE == 3) sparse_phase<T>(mv, p, st, a.sp, a.partM, a.partC, vs, red_smem); \
   else dense2_phase<T, MODE == 2>(mv, a.plan2, st, a.d2, vs);
 #define CLP_GATHER()                                                                        \
-  if constexpr (MODE == 0) gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv); \
+  if constexpr (MODE == 0 || MODE == 3) gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv); \
   else dense2_gather(mv, a.plan2, a.d2, lr, Mv, Cv);
 #define CLP_SUMV(out)                                                                       \
-  if constexpr (MODE == 0) { out = 0.0; for (int s_ = 0; s_ < p.NSEG; ++s_) out += __ldcg(a.segsum + s_); } \
+  if constexpr (MODE == 0 || MODE == 3) { out = 0.0; for (int s_ = 0; s_ < p.NSEG; ++s_) out += __ldcg(a.segsum + s_); } \
   else out = block_sum_ordered(a.d2.sumpart, a.plan2.G, red_smem);
 #define CLP_EXCHANGE()                                                                      \
   CLP_LAP(ns_cb);                                                                           \

@@ -176,13 +176,19 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
 /* CTAs of the persistent solver per SM (1 or 2, default 2). 1 lets two shards share one GPU,
  * which is how the sharded path is exercised on a single-GPU box. */
 int clp_set_ctas_per_sm(clp_handle h, int n);
-/* How the solver / mat-vec sweep the dense matrix:
- *   2 (default on unsharded handles): column stripes, ONLY the upper triangle is read and every element
- *     is applied two-sidedly in-tile -> ~2 m^2 bytes per objective evaluation (fp32 storage);
- *   1: column stripes, full matrix (4 m^2 bytes; what sharded handles use);
- *   0: first-generation column-segment decomposition, full matrix. */
+/* How the solver / mat-vec sweep the matrix (the dense store always exists; getters read it):
+ *   4 (default) auto: 3 when the graph is sparse enough for the compact copy to move fewer bytes than the
+ *     best dense sweep (x0.8), else 2 on an unsharded handle / 0 on a sharded one;
+ *   3: compact rows -- after the dense build the non-neutral entries of every row are packed in column
+ *     order as (fp32 value, 16-bit column): 6 bytes per kept entry per objective evaluation;
+ *   2: column stripes, ONLY the upper triangle is read and every element is applied two-sidedly in-tile
+ *     -> ~2 m^2 bytes per objective evaluation (fp32 storage), single GPU;
+ *   1: column stripes, full matrix (4 m^2 bytes);
+ *   0: first-generation column-segment decomposition, full matrix (4 m^2 bytes). */
 int clp_set_dense_mode(clp_handle h, int mode);
 int clp_get_dense_mode(clp_handle h, int* requested, int* effective);
+/* entries kept by the compact copy (all local rows) and the algorithmic bytes one sparse pass reads */
+int clp_sparse_info(clp_handle h, int64_t* nnz_kept, int64_t* bytes_per_pass);
 
 #ifdef __cplusplus
 }

@@ -440,8 +440,9 @@ def test_full_size_c2_properties(clp):
 @pytest.mark.parametrize("storage", [0, 1])
 @pytest.mark.parametrize("m", [7, 100, 2047, 2049, 4500, 6200])
 def test_dense_modes_agree(clp, orc, m, storage):
-    """mode 2 reads only the upper triangle (two-sided in-tile update); modes 1 / 0 read the full matrix.
-    Sizes straddle the 2048-column stripe boundary and the diagonal-block logic."""
+    """mode 2 reads only the upper triangle (two-sided in-tile update); modes 1 / 0 read the full matrix;
+    mode 3 sweeps the compact-row copy; 4 picks automatically.  Sizes straddle the 2048-column stripe
+    boundary, the diagonal-block logic and the 128-column segment steps."""
     from clipper_b200 import datagen
     prob = datagen.config_problem("c2", m); cfg = prob["cfg"]
     o = orc.Oracle()
@@ -450,14 +451,14 @@ def test_dense_modes_agree(clp, orc, m, storage):
     rng = np.random.default_rng(m)
     v = rng.random(m)
     res = []
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3, 4):
         c = make_euclid(clp, sigma=cfg["sigma"], epsilon=cfg["epsilon"], storage=storage)
         c.set_dense_mode(mode)
         c.score_pairwise_consistency(prob["D1"], prob["D2"], prob["A"])
         y, Mv, Cv = c.matvec(v, 0.6)
         c.solve(prob["u0"]); s = c.get_solution()
         res.append((y, Mv, Cv, s))
-    for k in (1, 2):
+    for k in (1, 2, 3, 4):
         assert np.abs(res[k][1] - res[0][1]).max() <= 1e-12 * max(1.0, np.abs(res[0][1]).max())
         assert np.abs(res[k][2] - res[0][2]).max() <= 1e-12 * max(1.0, np.abs(res[0][2]).max())
         assert np.abs(res[k][0] - res[0][0]).max() <= 1e-12 * max(1.0, np.abs(res[0][0]).max())
@@ -468,3 +469,29 @@ def test_dense_modes_agree(clp, orc, m, storage):
     for _, _, _, s in res:
         assert sorted(s.nodes) == sorted(so.nodes.tolist())
         assert abs(s.score - so.score) <= (1e-9 if storage == 1 else 1e-5) * abs(so.score)
+
+
+@pytest.mark.parametrize("storage", [0, 1])
+def test_compact_rows_keep_every_non_neutral_entry(clp, orc, storage):
+    """mode 3 must keep (M=0,C=1) and (M>0,C=0) entries -- only the -0.0 code is dropped"""
+    rng = np.random.default_rng(21)
+    m = 300
+    M = np.triu(rng.random((m, m)) * (rng.random((m, m)) < 0.2), 1)
+    C = np.triu((rng.random((m, m)) < 0.4).astype(np.float64), 1)
+    M = M + M.T + np.eye(m); C = C + C.T + np.eye(m)
+    o = orc.Oracle(); o.set_matrix_data(M, C)
+    c = make_euclid(clp, storage=storage); c.set_dense_mode(3); c.set_matrix_data(M, C)
+    assert c.dense_mode() == 3
+    kept, nbytes = c.sparse_info()
+    union = ((np.triu(M, 1) != 0) | (np.triu(C, 1) != 0)).sum() * 2
+    assert kept == union
+    v = rng.random(m)
+    y, Mv, Cv = c.matvec(v, 1.1); yo, _ = o.gradf(v, 1.1)
+    assert np.abs(y - yo).max() <= (1e-12 if storage else 1e-5) * np.abs(yo).max()
+    assert np.abs(Cv - o.matvec(v, 1)).max() <= 1e-12 * np.abs(Cv).max()
+    u0 = rng.random(m)
+    c.solve(u0); so = o.solve(u0)
+    assert sorted(c.get_solution().nodes) == sorted(so.nodes.tolist())
+    # switching the sweep on an existing matrix re-finalises it
+    c.set_dense_mode(0); y0, _, _ = c.matvec(v, 1.1)
+    assert np.abs(y0 - y).max() <= 1e-12 * np.abs(y).max()
