@@ -52,7 +52,10 @@ struct clp_handle_s {
   clp_params prm;
   std::string err;
   int sm_count = 0;
-  int ctas_per_sm = 2;
+  int ctas_per_sm = 2;       // dense sweeps (and the user cap set by clp_set_ctas_per_sm)
+  int ctas_sparse = 3;       // compact-row sweep: latency-bound, few registers -> 3 CTAs per SM
+  int ctas_cap = 3;          // user cap (clp_set_ctas_per_sm)
+  int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? ctas_sparse : ctas_per_sm); }
 
   // sharding (row block [row0,row0+rows) of the m x m matrix lives here)
   int rank = 0, world = 1;
@@ -97,7 +100,7 @@ struct clp_handle_s {
                           //            3 compact rows, 4 auto (compact rows when the graph is sparse enough, else 2 / 0)
   int dense_mode_eff = 2; // effective, decided when the matrix is finalised
   // compact-row copy (clp_sparse.cuh)
-  DevBuf sp_val, sp_col, sp_rowptr, sp_segoff, sp_rowcnt;
+  DevBuf sp_val, sp_col, sp_ptr4;
   unsigned long long sp_nnz = 0, sp_nnz_real = 0;
   SparseView sp{};
   Plan2 plan2{};
@@ -163,7 +166,7 @@ Plan make_plan(long long m, int rows_pad, int G) {
 
 // stripe decomposition: item enumeration, per-CTA runs, buffers (clp_dense2.cuh)
 int build_plan2(clp_handle h) {
-  const int G = h->sm_count * h->ctas_per_sm;
+  const int G = h->plan.G;
   Plan2& p = h->plan2;
   p.G = G;
   p.sym = h->dense_mode_eff == 2 ? 1 : 0;
@@ -241,50 +244,60 @@ template <typename T>
 int build_sparse(clp_handle h, bool force) {
   const Plan& p = h->plan;
   const int nseg = p.NSEG;
-  CLP_CUDA(h, h->sp_segoff.ensure((size_t)h->rows_pad * (nseg + 1) * sizeof(unsigned int)));
-  CLP_CUDA(h, h->sp_rowcnt.ensure((size_t)h->rows_pad * sizeof(unsigned long long)));
-  CLP_CUDA(h, h->sp_rowptr.ensure(((size_t)h->rows_pad + 1) * sizeof(unsigned long long)));
-  const T* M = h->Mbuf.as<T>();
-  const unsigned blocks = (unsigned)(((size_t)h->rows_pad * 32 + 255) / 256);
+  const long long nptr = (long long)nseg * (h->rows_pad + 1);
+  CLP_CUDA(h, h->sp_ptr4.ensure((size_t)nptr * sizeof(unsigned int)));
+  CLP_CUDA(h, cudaMemsetAsync(h->sp_ptr4.p, 0, (size_t)nptr * sizeof(unsigned int), h->stream));
   if (int rc = reset_sync(h)) return rc;
   SyncBlock* sb = h->sync.as<SyncBlock>();
+  const T* M = h->Mbuf.as<T>();
+  const unsigned blocks = (unsigned)(((size_t)h->rows_pad * 32 + 255) / 256);
   sparse_count_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
-                                                        h->sp_segoff.as<unsigned int>(), h->sp_rowcnt.as<unsigned long long>(),
-                                                        &sb->counts[0]);
+                                                        h->sp_ptr4.as<unsigned int>(), &sb->counts[0]);
   CLP_CUDA(h, cudaGetLastError());
-  sparse_scan_kernel<<<1, 1024, 0, h->stream>>>(h->sp_rowcnt.as<unsigned long long>(), h->rows_pad,
-                                                 h->sp_rowptr.as<unsigned long long>());
+  unsigned long long* total4_d = reinterpret_cast<unsigned long long*>(&sb->leaf[0][0]);  // scratch word of the sync block
+  sparse_scan_kernel<<<1, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), nptr, total4_d);
   CLP_CUDA(h, cudaGetLastError());
-  unsigned long long nnz = 0, nreal = 0;
-  CLP_CUDA(h, cudaMemcpyAsync(&nnz, h->sp_rowptr.as<unsigned long long>() + h->rows_pad, sizeof(nnz), cudaMemcpyDeviceToHost, h->stream));
-  CLP_CUDA(h, cudaMemcpyAsync(&nreal, &sb->counts[0], sizeof(nreal), cudaMemcpyDeviceToHost, h->stream));
+  unsigned long long host[3] = {0, 0, 0};
+  CLP_CUDA(h, cudaMemcpyAsync(&host[0], total4_d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CLP_CUDA(h, cudaMemcpyAsync(&host[1], &sb->counts[0], 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CLP_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->sp_nnz = nnz;        // stored entries (slices padded to multiples of 4): what one pass reads
-  h->sp_nnz_real = nreal; // non-neutral entries of the local rows
+  const unsigned long long n4 = host[0];
+  if (n4 >= 0xffffffffull) { if (force) return fail(h, CLP_ERR_UNSUPPORTED, "compact rows: too many entries"); return 1; }
+  h->sp_nnz = 4 * n4;        // stored entries (slices padded to multiples of 4): what one pass reads
+  h->sp_nnz_real = host[1];  // non-neutral entries of the local rows
+  h->sp.plain = host[2] == 0 ? 1 : 0;
   // worth it?  compare with the bytes of the best dense sweep (upper triangle two-sided on one GPU, full rows when sharded)
-  const double sparse_bytes = (double)nnz * (sizeof(T) + 2.0);
+  const double sparse_bytes = (double)h->sp_nnz * (sizeof(T) + 2.0);
   const double dense_bytes = (h->world > 1) ? (double)sizeof(T) * h->rows * (double)h->m : 0.5 * sizeof(T) * (double)h->m * (double)h->m;
   if (!force && !(sparse_bytes < 0.8 * dense_bytes)) return 1;  // keep a dense sweep
-  CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(nnz, 1) * sizeof(T)));
-  CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(nnz, 1) * sizeof(unsigned short)));
-  sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, p.W, nseg, h->sp_rowptr.as<unsigned long long>(),
-                                                       h->sp_segoff.as<unsigned int>(), h->sp_val.as<T>(), h->sp_col.as<unsigned short>());
+  CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(T)));
+  CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(unsigned short)));
+  sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
+                                                       h->sp_ptr4.as<unsigned int>(), h->sp_val.as<T>(), h->sp_col.as<unsigned short>());
   CLP_CUDA(h, cudaGetLastError());
-  h->sp.val = h->sp_val.p; h->sp.col16 = h->sp_col.as<unsigned short>();
-  h->sp.row_ptr = h->sp_rowptr.as<unsigned long long>(); h->sp.seg_off = h->sp_segoff.as<unsigned int>();
-  h->sp.nseg = nseg;
+  h->sp.val = h->sp_val.p; h->sp.off16 = h->sp_col.as<unsigned short>();
+  h->sp.ptr4 = h->sp_ptr4.as<unsigned int>(); h->sp.rows_pad = h->rows_pad;
+  return CLP_OK;
+}
+
+int set_plan_for(clp_handle h, int mode) {
+  h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_for(mode));
+  CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
+  CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
   return CLP_OK;
 }
 
 int finalize_matrix(clp_handle h) {
   int eff = h->dense_mode;
   if (eff == 3 || eff == 4) {
+    if (int rc = set_plan_for(h, 3)) return rc;  // the compact copy is cut along this plan's column segments
     const int rc = (h->storage == CLP_STORE_F64) ? build_sparse<double>(h, eff == 3) : build_sparse<float>(h, eff == 3);
     if (rc == CLP_OK) eff = 3;
     else if (rc == 1) eff = (h->world > 1) ? 0 : 2;
     else return rc;
   }
   if (eff == 2 && h->world > 1) eff = 1;
+  if (eff != 3) { if (int rc = set_plan_for(h, eff)) return rc; }
   h->dense_mode_eff = eff;
   if (eff == 1 || eff == 2) { if (int rc = build_plan2(h)) return rc; }
   return CLP_OK;
@@ -301,7 +314,7 @@ int ensure_matrix(clp_handle h, long long m) {
   h->ld = round_up(m, 128);
   h->mpad = round_up(m, 128);
   CLP_CUDA(h, h->Mbuf.ensure((size_t)h->rows_pad * (size_t)h->ld * h->esize()));
-  h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_per_sm);
+  h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_for(h->dense_mode == 3 || h->dense_mode == 4 ? 3 : h->dense_mode));
   // workspace
   CLP_CUDA(h, h->vecs.ensure((size_t)V_SLOTS * h->mpad * sizeof(double)));
   {
@@ -609,24 +622,25 @@ int clp_create(int device, int storage, clp_handle* out) {
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = h->sync.ensure(sizeof(SyncBlock))) != cudaSuccess) return bail("cudaMalloc", e);
-  int occ = 0;
+  int occ = 0, occ3 = 0;
   {
     int o0 = 0, o1 = 0, o2 = 0;
     if (storage == CLP_STORE_F64) {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, solver_kernel<double, 0>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, solver_kernel<double, 1>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, solver_kernel<double, 2>, kThreads, 0);
-      if (e == cudaSuccess) { int o3 = 0; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, solver_kernel<double, 3>, kThreads, 0); o2 = std::min(o2, o3); }
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, solver_kernel<double, 3>, kThreads, 0);
     } else {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, solver_kernel<float, 0>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, solver_kernel<float, 1>, kThreads, 0);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, solver_kernel<float, 2>, kThreads, 0);
-      if (e == cudaSuccess) { int o3 = 0; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, solver_kernel<float, 3>, kThreads, 0); o2 = std::min(o2, o3); }
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, solver_kernel<float, 3>, kThreads, 0);
     }
     occ = std::min(o0, std::min(o1, o2));
   }
-  if (e != cudaSuccess || occ < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
+  if (e != cudaSuccess || occ < 1 || occ3 < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
   h->ctas_per_sm = std::min(occ, 2);
+  h->ctas_sparse = std::min(occ3, 3);
   *out = h;
   return CLP_OK;
 }
@@ -637,7 +651,7 @@ int clp_destroy(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r)
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
-  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_rowptr, &h->sp_segoff, &h->sp_rowcnt, &h->parts, &h->small,
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->parts, &h->small,
                     &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -988,14 +1002,12 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
 }
 
 int clp_set_ctas_per_sm(clp_handle h, int n) {
-  if (!h || n < 1 || n > 2) return fail(h, CLP_ERR_INVALID, "ctas_per_sm must be 1 or 2");
-  h->ctas_per_sm = n;
+  if (!h || n < 1 || n > 3) return fail(h, CLP_ERR_INVALID, "ctas_per_sm must be 1, 2 or 3");
+  h->ctas_cap = n;
   if (h->m > 0) {
-    h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_per_sm);
     CLP_CUDA(h, cudaSetDevice(h->device));
-    CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
-    CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
     if (h->has_matrix) { if (int rc = finalize_matrix(h)) return rc; }
+    else { if (int rc = set_plan_for(h, h->dense_mode == 3 || h->dense_mode == 4 ? 3 : h->dense_mode)) return rc; }
   }
   return CLP_OK;
 }
@@ -1004,7 +1016,7 @@ int clp_sparse_info(clp_handle h, int64_t* nnz_kept, int64_t* bytes_per_pass) {
   if (!h) return CLP_ERR_INVALID;
   if (nnz_kept) *nnz_kept = (int64_t)h->sp_nnz_real;
   if (bytes_per_pass)
-    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) + (unsigned long long)h->rows * ((h->plan.NSEG + 1) * 4 + 8));
+    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) + (unsigned long long)(h->rows + 1) * h->plan.NSEG * 4);
   return CLP_OK;
 }
 

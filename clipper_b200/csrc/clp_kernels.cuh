@@ -577,9 +577,9 @@ __global__ void matvec_combine_kernel(MatView mv, Plan p, const double* partM, c
 
 // sparse sweep (clp_sparse.cuh); the combine step is matvec_combine_kernel
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 matvec_sparse_partials_kernel(MatView mv, Plan p, StageArgs st, SparseView sp, double* partM, double* partC) {
-  __shared__ __align__(16) double vs[kSegMax];
+  __shared__ __align__(16) double vs[kSegMax + 2];
   __shared__ double red_smem[kWarps];
   sparse_phase<T>(mv, p, st, sp, partM, partC, vs, red_smem);
 }
@@ -781,8 +781,8 @@ __device__ bool exchange_sums(const SolverArgs& a, const double (&loc)[kRedVals]
 // MODE 0: column-segment decomposition (matvec_phase); 1: stripes, full matrix; 2: stripes, upper triangle
 // read once and applied two-sidedly (single GPU); 3: compact rows (clp_sparse.cuh) in the MODE-0 decomposition
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) solver_kernel(SolverArgs a) {
-  __shared__ __align__(16) double vs[kSegMax];
+__global__ void __launch_bounds__(kThreads, MODE == 3 ? 3 : 2) solver_kernel(SolverArgs a) {
+  __shared__ __align__(16) double vs[kSegMax + 2];
   __shared__ double red_smem[kWarps * kRedVals + kMaxPeers * kRedVals];
   __shared__ int smem_flag;
   const MatView& mv = a.mv;

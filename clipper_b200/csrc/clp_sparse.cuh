@@ -1,26 +1,34 @@
-// clp_sparse.cuh -- compact-row ("bit-dropped") copy of the affinity matrix and its sweep.
+// clp_sparse.cuh -- compact-row copy of the affinity matrix and its sweep.
 //
-// SURVEY section 8f rank 3.  The consistency graph is sparse (14.9 % at BASELINE.json's config 2), so
-// after the dense build the non-neutral entries (everything except the -0.0 "inconsistent" code) of every
-// local row are compacted, in column order, into
-//      val[]   : the stored element itself (fp32 / fp64, sign bit = constraint bit, as in the dense store)
-//      col16[] : the column, relative to the start of its column segment (segments are <= 4096 wide)
-// = 6 bytes per kept entry (fp32 storage) instead of 4 bytes per matrix element.  The sweep keeps the
-// first-generation decomposition (column segments staged in shared memory, 32-row tiles, per-segment
-// partial products, fixed-order combine): only the inner row sweep changes, from a dense stream to a
-// gather over the row's slice of entries that fall into the staged segment.
-//      slice(row, seg) = [ row_ptr[row] + seg_off[row][seg] , row_ptr[row] + seg_off[row][seg+1] )
-// Algorithmic bytes per objective evaluation: 6 * nnz (+ 4 (NSEG+1) + 8 bytes of offsets per row).
+// The consistency graph is sparse (14.9 % at BASELINE.json's config 2), so after the dense build the
+// non-neutral entries (everything except the -0.0 "inconsistent" code) of every local row are compacted,
+// in column order, into
+//      val[]  : the stored element itself (fp32 / fp64; sign bit = constraint bit, as in the dense store)
+//      off16[]: 8 * (column - first column of its segment) -- the byte offset of v[column] inside the
+//               shared-memory copy of the segment (segments are <= 4096 columns wide)
+// = 6 bytes per kept entry (fp32 storage) instead of 4 bytes per matrix element.
+// Layout is SEGMENT-major: all row slices of column segment 0, then segment 1, ...; inside a segment the
+// slices of consecutive rows are adjacent, so the 32 rows x 1 segment a CTA works on are one contiguous
+// range of HBM.  Every slice is padded to a multiple of 4 entries (16-byte value loads); padding entries
+// point at a zero slot behind the staged segment.  slice(row, seg) in units of 4 entries:
+//      [ ptr4[seg * (rows_pad + 1) + row] , ptr4[seg * (rows_pad + 1) + row + 1] )
+// The sweep keeps the first-generation decomposition (segments of v staged in shared memory, 32-row tiles,
+// per-segment partial products, fixed-order combine); only the inner row sweep changes.
+// "plain" matrices (every kept entry has M > 0 and C = 1 -- always true after scorePairwiseConsistency) take
+// a shorter path: Chat v is then just the sum of the gathered v.
+// Algorithmic bytes per objective evaluation: 6 * stored entries + 4 * NSEG * (rows + 1).
 #pragma once
 
 namespace clp {
 
+constexpr unsigned int kZeroSlot = kSegMax * 8;  // byte offset of the zero element behind the staged segment
+
 struct SparseView {
-  const void* val;                  // T [nnz]
-  const unsigned short* col16;      // [nnz] column - seg * W
-  const unsigned long long* row_ptr;  // [rows_pad + 1]
-  const unsigned int* seg_off;      // [rows_pad][NSEG + 1] offsets of the row's segment slices
-  int nseg;
+  const void* val;             // T [4 * n4]
+  const unsigned short* off16; // [4 * n4]
+  const unsigned int* ptr4;    // [NSEG][rows_pad + 1]
+  int rows_pad;
+  int plain;                   // every kept entry has M > 0 and C = 1
 };
 
 template <typename T> __device__ __forceinline__ bool is_neutral(T s);
@@ -28,71 +36,70 @@ template <> __device__ __forceinline__ bool is_neutral<float>(float s) { return 
 template <> __device__ __forceinline__ bool is_neutral<double>(double s) {
   return (unsigned long long)__double_as_longlong(s) == 0x8000000000000000ULL;
 }
+template <typename T> __device__ __forceinline__ bool is_plain(T s) { return s > T(0); }
 
-// pass 1: one warp per local row counts the kept entries per column segment.  Every (row, segment) slice is
-// padded to a multiple of 4 entries so that the sweep can use 16-byte value loads; seg_off holds the padded
-// exclusive prefix inside the row, row_cnt the padded row total, *real_total the number of real entries.
+// pass 1: one warp per (padded) local row counts the kept entries per column segment:
+//   cnt4[seg * (rows_pad + 1) + row] = number of 4-entry units of slice (row, seg)
+//   totals[0] += kept entries, totals[1] += kept entries that are not "plain"
 template <typename T>
 __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
-                                    unsigned int* seg_off, unsigned long long* row_cnt, unsigned long long* real_total) {
+                                    unsigned int* cnt4, unsigned long long* totals) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows_pad) return;
-  unsigned int run = 0, real = 0;
+  unsigned int real = 0, odd = 0;
   for (int s = 0; s < nseg; ++s) {
-    unsigned int c = 0;
+    unsigned int c = 0, o = 0;
     if (warp < rows) {
       const int c0 = s * W, c1 = min(m, c0 + W);
       for (int j = c0 + lane * 4; j < c1; j += 128) {
         const T* p = M + (size_t)warp * ld + j;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) c += (j + e < c1 && !is_neutral<T>(p[e])) ? 1u : 0u;
+        for (int e = 0; e < 4; ++e)
+          if (j + e < c1 && !is_neutral<T>(p[e])) { ++c; o += is_plain<T>(p[e]) ? 0u : 1u; }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) seg_off[(size_t)warp * (nseg + 1) + s] = run;
-    real += c;
-    run += (c + 3u) & ~3u;
+    for (int k = 16; k > 0; k >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, k); o += __shfl_xor_sync(0xffffffffu, o, k); }
+    if (lane == 0) cnt4[(size_t)s * (rows_pad + 1) + warp] = (c + 3u) >> 2;
+    real += c; odd += o;
   }
   if (lane == 0) {
-    seg_off[(size_t)warp * (nseg + 1) + nseg] = run;
-    row_cnt[warp] = run;
-    if (real) atomicAdd(real_total, (unsigned long long)real);
+    if (real) atomicAdd(&totals[0], (unsigned long long)real);
+    if (odd) atomicAdd(&totals[1], (unsigned long long)odd);
   }
 }
 
-// pass 2: exclusive scan of the row counts (single block; rows_pad <= 262144)
-__global__ void sparse_scan_kernel(const unsigned long long* row_cnt, int n, unsigned long long* row_ptr) {
+// pass 2: exclusive scan of the n unit counts in place (single block; n <= 64 * 262145); total -> *total4
+__global__ void sparse_scan_kernel(unsigned int* cnt4, long long n, unsigned long long* total4) {
   __shared__ unsigned long long part[1024];
   const int t = threadIdx.x, nt = blockDim.x;
-  const int per = (n + nt - 1) / nt;
-  const int b = t * per, e = min(n, b + per);
+  const long long per = (n + nt - 1) / nt;
+  const long long b = t * per, e = (b + per < n) ? b + per : n;
   unsigned long long s = 0;
-  for (int i = b; i < e; ++i) s += row_cnt[i];
+  for (long long i = b; i < e; ++i) s += cnt4[i];
   part[t] = s;
   __syncthreads();
   if (t == 0) {
     unsigned long long run = 0;
     for (int i = 0; i < nt; ++i) { const unsigned long long v = part[i]; part[i] = run; run += v; }
-    row_ptr[n] = run;
+    *total4 = run;
   }
   __syncthreads();
   unsigned long long run = part[t];
-  for (int i = b; i < e; ++i) { row_ptr[i] = run; run += row_cnt[i]; }
+  for (long long i = b; i < e; ++i) { const unsigned int c = cnt4[i]; cnt4[i] = (unsigned int)run; run += c; }
 }
 
-// pass 3: one warp per row writes the kept entries of each segment in column order, then the padding
+// pass 3: one warp per row writes the kept entries of each segment in column order, then the padding.
+// ptr4 is the scanned array; the slot [seg][rows_pad] of every segment holds the start of the next one.
 template <typename T>
-__global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, int W, int nseg,
-                                   const unsigned long long* row_ptr, const unsigned int* seg_off, T* val,
-                                   unsigned short* col16) {
+__global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
+                                   const unsigned int* ptr4, T* val, unsigned short* off16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const unsigned long long base = row_ptr[warp];
-  const unsigned int* so = seg_off + (size_t)warp * (nseg + 1);
   for (int s = 0; s < nseg; ++s) {
-    unsigned long long pos = base + so[s];
-    const unsigned long long slice_end = base + so[s + 1];
+    const unsigned int* pp = ptr4 + (size_t)s * (rows_pad + 1) + warp;
+    unsigned long long pos = 4ull * pp[0];
+    const unsigned long long slice_end = 4ull * pp[1];
     const int c0 = s * W, c1 = min(m, c0 + W);
     for (int j0 = c0; j0 < c1; j0 += 128) {
       const int j = j0 + lane * 4;
@@ -114,10 +121,10 @@ __global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, in
       unsigned long long w = pos + (pre - cnt);
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (keep & (1u << e)) { val[w] = x[e]; col16[w] = (unsigned short)(j + e - c0); ++w; }
+        if (keep & (1u << e)) { val[w] = x[e]; off16[w] = (unsigned short)(8 * (j + e - c0)); ++w; }
       pos += total;
     }
-    for (unsigned long long w = pos + lane; w < slice_end; w += 32) { val[w] = encode<T>(0.0, false); col16[w] = 0; }
+    for (unsigned long long w = pos + lane; w < slice_end; w += 32) { val[w] = encode<T>(0.0, false); off16[w] = (unsigned short)kZeroSlot; }
   }
 }
 
@@ -125,92 +132,93 @@ __global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, in
 template <typename T> struct Entry4;
 template <> struct Entry4<float> {
   float4 x; uint2 k;
-  __device__ __forceinline__ void load(const float* val, const unsigned short* col, unsigned long long at) {
+  __device__ __forceinline__ void load(const float* val, const unsigned short* off, unsigned long long at) {
     x = ldg_stream(reinterpret_cast<const float4*>(val + at));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(col + at));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(off + at));
   }
-  __device__ __forceinline__ void neutral() { x = make_float4(-0.f, -0.f, -0.f, -0.f); k = make_uint2(0u, 0u); }
   __device__ __forceinline__ float get(int e) const { return e == 0 ? x.x : e == 1 ? x.y : e == 2 ? x.z : x.w; }
+  __device__ __forceinline__ void neutral() { x = make_float4(-0.f, -0.f, -0.f, -0.f); k = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16)); }
 };
 template <> struct Entry4<double> {
   double2 a, b; uint2 k;
-  __device__ __forceinline__ void load(const double* val, const unsigned short* col, unsigned long long at) {
+  __device__ __forceinline__ void load(const double* val, const unsigned short* off, unsigned long long at) {
     a = ldg_stream(reinterpret_cast<const double2*>(val + at));
     b = ldg_stream(reinterpret_cast<const double2*>(val + at) + 1);
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(col + at));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(off + at));
   }
-  __device__ __forceinline__ void neutral() { a = make_double2(-0.0, -0.0); b = a; k = make_uint2(0u, 0u); }
   __device__ __forceinline__ double get(int e) const { return e == 0 ? a.x : e == 1 ? a.y : e == 2 ? b.x : b.y; }
+  __device__ __forceinline__ void neutral() { a = make_double2(-0.0, -0.0); b = a; k = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16)); }
 };
-__device__ __forceinline__ unsigned int col_of(const uint2& k, int e) {
+__device__ __forceinline__ unsigned int off_of(const uint2& k, int e) {
   return e == 0 ? (k.x & 0xffffu) : e == 1 ? (k.x >> 16) : e == 2 ? (k.y & 0xffffu) : (k.y >> 16);
 }
+__device__ __forceinline__ double vs_at(const double* vs, unsigned int byte_off) {
+  return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(vs) + byte_off);
+}
 
-// 2 x 4 rows (rows [lra, lra+4) and [lrb, lrb+4); lrb < 0: none) x the staged segment.  The eight row slices
-// are walked together; every lane takes chunks of 4 consecutive entries, so up to 8 x (16 + 8) bytes per lane
-// are in flight.  vs holds the segment of v in natural order.
-template <typename T>
-__device__ __forceinline__ void sparse_rows8(const SparseView& sp, int lra, int lrb, int seg, const double* vs,
-                                             double (&accA)[8], double (&accB)[8]) {
+// rows [lr, lr+4) x the staged segment.  The four row slices are walked together; every lane takes chunks of
+// 4 consecutive entries (4 x (16 + 8) bytes per lane in flight).  Few registers on purpose: the sweep is
+// latency-bound, so the kernels that contain it run 3 CTAs per SM.
+// vs holds the segment of v in natural order, vs[kSegMax] == 0.
+template <typename T, bool PLAIN>
+__device__ __forceinline__ void sparse_rows4(const SparseView& sp, int lr, int seg, const double* vs,
+                                             double (&acc)[8]) {
   const int lane = threadIdx.x & 31;
   const T* val = reinterpret_cast<const T*>(sp.val);
-  unsigned long long beg[8];
-  unsigned int n4[8], nmax = 0;
+  const unsigned int* pa = sp.ptr4 + (size_t)seg * (sp.rows_pad + 1) + lr;
+  unsigned int beg[4], n4[4], nmax = 0;
+  {
+    unsigned int a[5];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = (r < 4) ? lra + r : lrb + (r - 4);
-    n4[r] = 0; beg[r] = 0;
-    if (r < 4 || lrb >= 0) {
-      const unsigned long long base = sp.row_ptr[row];
-      const unsigned int* so = sp.seg_off + (size_t)row * (sp.nseg + 1) + seg;
-      const unsigned int o0 = so[0], o1 = so[1];
-      beg[r] = base + o0;
-      n4[r] = (o1 - o0) >> 2;
-      nmax = max(nmax, n4[r]);
-    }
+    for (int r = 0; r < 5; ++r) a[r] = pa[r];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { beg[r] = a[r]; n4[r] = a[r + 1] - a[r]; nmax = max(nmax, n4[r]); }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { accA[i] = 0.0; accB[i] = 0.0; }
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
   for (unsigned int c = lane; c < nmax; c += 32) {
-    Entry4<T> E[8];
+    Entry4<T> E[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (c < n4[r]) E[r].load(val, sp.col16, beg[r] + 4ull * c);
+    for (int r = 0; r < 4; ++r) {
+      if (c < n4[r]) E[r].load(val, sp.off16, 4ull * (beg[r] + c));
       else E[r].neutral();
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const double v = vs[col_of(E[r].k, e)];
-        double dummyM = 0.0, dummyC = 0.0;
-        if (r < 4) apply_elem<false>(E[r].get(e), v, 0.0, accA[r], accA[4 + r], dummyM, dummyC);
-        else apply_elem<false>(E[r].get(e), v, 0.0, accB[r - 4], accB[r], dummyM, dummyC);
+        const double v = vs_at(vs, off_of(E[r].k, e));
+        if (PLAIN) {
+          acc[r] = fma((double)E[r].get(e), v, acc[r]);  // padding: -0.0 * 0.0
+          acc[4 + r] += v;
+        } else {
+          double dummyM = 0.0, dummyC = 0.0;
+          apply_elem<false>(E[r].get(e), v, 0.0, acc[r], acc[4 + r], dummyM, dummyC);
+        }
       }
   }
 }
 
-// whole sparse pass of one CTA: same decomposition and partial layout as matvec_phase; a warp works on the
-// row slices of two of its row tiles at a time
+// whole sparse pass of one CTA: same decomposition and partial layout as matvec_phase.
+// vs must hold kSegMax + 1 doubles.
 template <typename T>
 __device__ void sparse_phase(const MatView& mv, const Plan& p, const StageArgs& st, const SparseView& sp,
                              double* partM, double* partC, double* vs, double* red_smem) {
   const int sg = blockIdx.x % p.SG, rg = blockIdx.x / p.SG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) vs[kSegMax] = 0.0;
   for (int seg = sg; seg < p.NSEG; seg += p.SG) {
     stage_segment<double>(st, p, mv.m, seg, rg == 0, vs, red_smem);  // <double>: natural (unpermuted) order
-    for (int rt = rg; rt < p.NRT; rt += 2 * p.RG) {
-      const int lra = rt * kRowTile + warp * kRowsPerWarp;
-      const int lrb = (rt + p.RG < p.NRT) ? (rt + p.RG) * kRowTile + warp * kRowsPerWarp : -1;
-      double accA[8], accB[8];
-      sparse_rows8<T>(sp, lra, lrb, seg, vs, accA, accB);
-      const double totA = warp_reduce8(accA);
-      const double totB = warp_reduce8(accB);
+    for (int rt = rg; rt < p.NRT; rt += p.RG) {
+      const int lr = rt * kRowTile + warp * kRowsPerWarp;
+      double acc[8];
+      if (sp.plain) sparse_rows4<T, true>(sp, lr, seg, vs, acc);
+      else sparse_rows4<T, false>(sp, lr, seg, vs, acc);
+      const double tot = warp_reduce8(acc);
       if ((lane & 3) == 0) {
         const int qv = lane >> 2;  // 0..3: M of row qv, 4..7: C of row qv-4
         double* dst = (qv >> 2) ? partC : partM;
-        dst[(size_t)seg * mv.rows_pad + lra + (qv & 3)] = totA;
-        if (lrb >= 0) dst[(size_t)seg * mv.rows_pad + lrb + (qv & 3)] = totB;
+        dst[(size_t)seg * mv.rows_pad + lr + (qv & 3)] = tot;
       }
     }
     __syncthreads();  // vs is re-staged by the next segment pass

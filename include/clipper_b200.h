@@ -173,8 +173,9 @@ int clp_shard_export(clp_handle h, void* blob, int64_t blob_bytes, int64_t* writ
 /* blobs: world blobs in rank order, blob_bytes_each apart (CUDA IPC between processes, plain
  * peer access when the exporting handle lives in the calling process). */
 int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, int world);
-/* CTAs of the persistent solver per SM (1 or 2, default 2). 1 lets two shards share one GPU,
- * which is how the sharded path is exercised on a single-GPU box. */
+/* Cap on the CTAs of the persistent solver per SM (1..3; default: 2 for the dense sweeps, 3 for the
+ * compact-row sweep). 1 lets two shards share one GPU, which is how the sharded path is exercised on
+ * a single-GPU box. */
 int clp_set_ctas_per_sm(clp_handle h, int n);
 /* How the solver / mat-vec sweep the matrix (the dense store always exists; getters read it):
  *   4 (default) auto: 3 when the graph is sparse enough for the compact copy to move fewer bytes than the
