@@ -195,6 +195,8 @@ def run_ours(args):
     h = clip.handle
     if os.environ.get("CLP_DENSE_MODE"):
         clip.set_dense_mode(int(os.environ["CLP_DENSE_MODE"]))
+    if os.environ.get("CLP_CTAS_PER_SM"):
+        _capi.check(h, L.clp_set_ctas_per_sm(h, int(os.environ["CLP_CTAS_PER_SM"])))
     stream = torch.cuda.current_stream()
     clip.set_stream(stream.cuda_stream)
 
@@ -297,6 +299,14 @@ def run_ours(args):
                "same_inlier_set": sorted(info["nodes"]) == sorted(nodes_dev),
                "rel_dF": abs(info["score"] - F_dev) / abs(info["score"])}
 
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if args.m is None:
+            traffic = tj[args.workload][str(mode)]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -319,8 +329,9 @@ def run_ours(args):
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": 3 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "solver_kernel<float> (persistent; %d dense passes of M per launch)"
-                                                % int(round(np.mean(n_matvec))), "peak_source": peak_src},
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "solver_kernel<float,%d> (persistent; %d passes over the matrix per launch)"
+                               % (mode, int(round(np.mean(n_matvec)))), "peak_source": peak_src},
     }
     if cpu:
         line["cpu_baseline"] = cpu
@@ -336,6 +347,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--m", type=int, default=None, help="override the workload's m (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="N>1: skip the extra m=80000 measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

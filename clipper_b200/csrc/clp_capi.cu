@@ -281,7 +281,14 @@ int build_sparse(clp_handle h, bool force) {
 }
 
 int set_plan_for(clp_handle h, int mode) {
-  h->plan = make_plan(h->m, h->rows_pad, h->sm_count * h->ctas_for(mode));
+  int ctas = h->ctas_for(mode);
+  if (mode == 3 && ctas == 3) {
+    // 3 CTAs/SM only pay off when every CTA still gets several 32-row tiles; measured at m=20000:
+    // 1 GPU (625 tiles) 3 > 2 CTAs/SM, 8 GPUs (79 tiles per shard) 2 > 3 > 1
+    const Plan p3 = make_plan(h->m, h->rows_pad, h->sm_count * 3);
+    if (p3.NRT < 4 * p3.RG) ctas = 2;
+  }
+  h->plan = make_plan(h->m, h->rows_pad, h->sm_count * ctas);
   CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
   CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
   return CLP_OK;

@@ -217,6 +217,10 @@ def run_bench(args, METRIC, UNIT):
         cfg = prob["cfg"]; m = cfg["m"]
         ip = clipperpy.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = cfg["sigma"], cfg["epsilon"]
         clip = ShardedCLIPPER(clipperpy.invariants.EuclideanDistance(ip), clipperpy.Params())
+        if os.environ.get("CLP_DENSE_MODE"):
+            clip.set_dense_mode(int(os.environ["CLP_DENSE_MODE"]))
+        if os.environ.get("CLP_CTAS_PER_SM"):
+            _capi.check(clip.handle, _capi.load().clp_set_ctas_per_sm(clip.handle, int(os.environ["CLP_CTAS_PER_SM"])))
         stream = torch.cuda.current_stream()
         clip.set_stream(stream.cuda_stream)
         D1 = torch.from_numpy(np.ascontiguousarray(prob["D1"].T)).to(dev)
@@ -252,7 +256,16 @@ def run_bench(args, METRIC, UNIT):
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks disagree on the solution"
+        mode = clip.dense_mode()
+        if mode == 3:
+            kept, pass_bytes = clip.sparse_info()      # this rank's rows
+        else:
+            r0, nrows = shard_rows(m, rank, world)
+            kept, pass_bytes = None, 4 * nrows * m
+        pb = torch.tensor([float(pass_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(pb, op=dist.ReduceOp.MAX)
         return dict(m=m, ms=float(t[0]), kernel_ms=float(t[1]), n_matvec=int(sol.n_matvec), n_evals=int(sol.n_evals),
+                    mode=mode, pass_bytes=float(pb[0]),
                     F=float(sol.score), n_nodes=int(sol.n_nodes), cfg=cfg,
                     phase_ms=dict(zip(("dense_passes", "combine", "exchange"), np.mean(prof, axis=0).tolist())))
 
@@ -266,7 +279,7 @@ def run_bench(args, METRIC, UNIT):
     peak, peak_src = measured_peaks()
     m = main["m"]
     value = m * args.steps / (main["ms"] * 1e-3)
-    alg = main["n_matvec"] * 4.0 * m * m / world   # algorithmic bytes per GPU per launch
+    alg = main["n_matvec"] * main["pass_bytes"]   # algorithmic bytes per GPU per launch (largest shard)
     ach = alg / (main["kernel_ms"] * 1e-3) / 1e9
     if rank == 0:
         line = {
@@ -276,7 +289,8 @@ def run_bench(args, METRIC, UNIT):
             "dtype": "f64 (f32 affinity storage, fp64 vectors/accumulators/decisions)", "data": "synthetic",
             "config": {"workload": "%s: synthetic EuclideanDistance m=%d, 95%% outliers, M row-sharded over %d GPUs, "
                                    "in-kernel NVLink peer-memory exchange" % (args.workload, m, world),
-                       "l2": "per-GPU slice of M = %.2f GB" % (4.0 * m * m / world / 1e9),
+                       "l2": "per-GPU dense slice of M = %.2f GB" % (4.0 * m * m / world / 1e9),
+                       "sweep_mode": main["mode"], "algorithmic_bytes_per_pass_per_gpu": main["pass_bytes"],
                        "evals_per_solve": main["n_evals"], "solver_kernel_ms": main["kernel_ms"],
                        "solver_phase_ms": main["phase_ms"], "F": main["F"],
                        "n_nodes": main["n_nodes"]},
@@ -293,7 +307,8 @@ def run_bench(args, METRIC, UNIT):
                                "value": m4 * max(1, min(3, args.steps)) / (extra["ms"] * 1e-3), "unit": UNIT,
                                "solver_kernel_ms": extra["kernel_ms"], "evals": extra["n_evals"],
                                "solver_phase_ms": extra["phase_ms"],
-                               "per_gpu_gbs": extra["n_matvec"] * 4.0 * m4 * m4 / world / (extra["kernel_ms"] * 1e-3) / 1e9,
+                               "per_gpu_gbs": extra["n_matvec"] * extra["pass_bytes"] / (extra["kernel_ms"] * 1e-3) / 1e9,
+                               "sweep_mode": extra["mode"],
                                "F": extra["F"], "n_nodes": extra["n_nodes"]}
         print(json.dumps(line))
     dist.barrier()
