@@ -359,15 +359,20 @@ int read_sync(clp_handle h, SyncBlock* sb) {
   return CLP_OK;
 }
 
-template <typename T>
-int launch_score(clp_handle h, int kind, int d, const ScoreArgs& a) {
+template <typename T, bool MIRROR>
+int launch_score_m(clp_handle h, int kind, int d, const ScoreArgs& a) {
   dim3 grid((unsigned)(h->ld / 128), (unsigned)(h->rows_pad / kRowTile));
-  if (kind == 1) score_tile_kernel<T, 1, 6><<<grid, kThreads, 0, h->stream>>>(a);
-  else if (d == 3) score_tile_kernel<T, 0, 3><<<grid, kThreads, 0, h->stream>>>(a);
-  else if (d == 2) score_tile_kernel<T, 0, 2><<<grid, kThreads, 0, h->stream>>>(a);
-  else score_tile_kernel<T, 0, 0><<<grid, kThreads, 0, h->stream>>>(a);
+  if (kind == 1) score_tile_kernel<T, 1, 6, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
+  else if (d == 3) score_tile_kernel<T, 0, 3, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
+  else if (d == 2) score_tile_kernel<T, 0, 2, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
+  else score_tile_kernel<T, 0, 0, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
   CLP_CUDA(h, cudaGetLastError());
   return CLP_OK;
+}
+template <typename T>
+int launch_score(clp_handle h, int kind, int d, const ScoreArgs& a) {
+  // an unsharded handle holds the whole symmetric matrix: compute the upper triangle, mirror the rest
+  return (h->world == 1) ? launch_score_m<T, true>(h, kind, d, a) : launch_score_m<T, false>(h, kind, d, a);
 }
 
 // common tail of the four scoring entry points: D1/D2/A already on the device

@@ -242,12 +242,16 @@ template <> struct Quad<double> {
 // One CTA = a 32-row x 128-column tile of the padded dense matrix; warp w owns 4 rows, lane l
 // owns 4 consecutive columns -> every row is written as 512 B (float) of consecutive float4.
 // KIND 0: EuclideanDistance with compile-time dimension D (D==0: runtime d). KIND 1: PointNormal.
-template <typename T, int KIND, int D>
+// MIRROR (unsharded handles): the score is symmetric in (i,j) bit for bit, so only tiles that touch the
+// upper triangle are computed; every value s(i,j), i<j, is stored at [i][j] (row-wise float4) and mirrored
+// to [j][i] (the lane's 4 rows of one column are 16 contiguous bytes of row j).  Halves the fp64 work.
+template <typename T, int KIND, int D, bool MIRROR>
 __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
   constexpr int DD = (KIND == 1) ? 6 : D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 128 + lane * 4;
   const int lr0 = blockIdx.y * kRowTile + warp * kRowsPerWarp;  // local row
+  if (MIRROR && (int)(blockIdx.x * 128 + 127) < (int)(blockIdx.y * kRowTile)) return;  // tile entirely below the diagonal
   T* Mbase = reinterpret_cast<T*>(a.M);
   const int dd = (DD > 0) ? DD : a.d;
 
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
   for (int e = 0; e < 4; ++e) {
     const int j = c0 + e;
     if (j >= a.m) continue;
+    if (MIRROR && j <= a.row0 + lr0) continue;  // column not right of any of this thread's rows
     const int aj0 = __ldg(a.A0 + j), aj1 = __ldg(a.A1 + j);
     double e1j[DD > 0 ? DD : 1], e2j[DD > 0 ? DD : 1];
     if (DD > 0) {
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
       const int li = lr0 + q;
       const int i = a.row0 + li;
       if (li >= a.rows || i == j) continue;
+      if (MIRROR && j < i) continue;  // lower triangle: written as the mirror of (j,i)
       const int ai0 = __ldg(a.A0 + i), ai1 = __ldg(a.A1 + i);
       if (ai0 == aj0 || ai1 == aj1) continue;  // distinctness (ref clipper.cpp:35-38)
       double scr;
@@ -297,10 +303,39 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
       if (scr > a.affinityeps) out[q][e] = encode<T>(scr, true);  // ref clipper.cpp:53-55
     }
   }
+  if (!MIRROR) {
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+      const int li = lr0 + q;
+      if (li < a.rows_pad && c0 < a.ld) Quad<T>::store(Mbase + (size_t)li * a.ld + c0, out[q]);
+    }
+    return;
+  }
+  // MIRROR: row0 == 0 and rows == m.  Row-wise stores of the part right of the diagonal (and the diagonal itself) ...
+  const int r0 = lr0;
 #pragma unroll
   for (int q = 0; q < kRowsPerWarp; ++q) {
-    const int li = lr0 + q;
-    if (li < a.rows_pad && c0 < a.ld) Quad<T>::store(Mbase + (size_t)li * a.ld + c0, out[q]);
+    const int i = r0 + q;
+    if (i >= a.rows_pad || c0 >= a.ld) continue;
+    if (c0 > i) Quad<T>::store(Mbase + (size_t)i * a.ld + c0, out[q]);
+    else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c0 + e >= i) Mbase[(size_t)i * a.ld + c0 + e] = out[q][e];
+    }
+  }
+  // ... and the mirror image: column j of this thread's 4 rows is 4 consecutive elements of row j
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = c0 + e;
+    if (j >= a.rows_pad) continue;
+    T col[4] = {out[0][e], out[1][e], out[2][e], out[3][e]};
+    if (r0 + 3 < j && r0 + 3 < a.ld) Quad<T>::store(Mbase + (size_t)j * a.ld + r0, col);
+    else {
+#pragma unroll
+      for (int q = 0; q < kRowsPerWarp; ++q)
+        if (r0 + q < j && r0 + q < a.ld) Mbase[(size_t)j * a.ld + r0 + q] = col[q];
+    }
   }
 }
 
