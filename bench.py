@@ -286,6 +286,18 @@ def run_ours(args):
     _capi.check(h, L.clp_matvec_dev(h, v.data_ptr(), 1.0, y.data_ptr(), None, None, 50, C.byref(ms_mv)))
     mv_gbs = (pass_bytes + 16 * m) / (ms_mv.value * 1e-3) / 1e9
 
+    # ---- the dense Md.v sweep of the same matrix (north_star: ">= 40 % of the HBM roofline on the Md.u mat-vec"):
+    #      switch this handle to the full-matrix dense sweep, time it alone, switch back
+    dense_ref = None
+    if mode != 0:
+        clip.set_dense_mode(0)
+        _capi.check(h, L.clp_matvec_dev(h, v.data_ptr(), 1.0, y.data_ptr(), None, None, 5, C.byref(ms_mv0 := C.c_double())))
+        _capi.check(h, L.clp_matvec_dev(h, v.data_ptr(), 1.0, y.data_ptr(), None, None, 50, C.byref(ms_mv0)))
+        g0 = (esz * m * m + 16 * m) / (ms_mv0.value * 1e-3) / 1e9
+        dense_ref = {"sweep": "segments, full dense fp32 matrix, 4 m^2 + 16 m bytes", "ms": ms_mv0.value, "GBps": g0,
+                     "frac_of_measured_hbm_peak": g0 / peak}
+        clip.set_dense_mode(int(os.environ.get("CLP_DENSE_MODE", "4")))
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1): one full oracle step (~10-30 s)
     cpu = None
     if not args.no_cpu_baseline:
@@ -323,7 +335,7 @@ def run_ours(args):
                    "solver_kernel_ms": kms,
                    "solver_phase_ms": dict(zip(("dense_passes", "combine", "exchange"), np.mean(prof, axis=0).tolist())),
                    "matvec_alone_gbs": mv_gbs, "matvec_alone_ms": ms_mv.value,
-                   "matvec_alone_frac": mv_gbs / peak, "F": F_dev, "n_nodes": len(nodes_dev)},
+                   "matvec_alone_frac": mv_gbs / peak, "dense_matvec_alone": dense_ref, "F": F_dev, "n_nodes": len(nodes_dev)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps},

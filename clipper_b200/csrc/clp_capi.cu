@@ -145,24 +145,24 @@ void shard_rows(long long m, int rank, int world, int* row0, int* rows) {
   *row0 = (int)r0; *rows = (int)std::max<long long>(0, r1 - r0);
 }
 
-// choose the CTA / segment decomposition of the mat-vec for this problem size
+// choose the CTA / segment decomposition of the mat-vec for this problem size.  The column segmentation
+// (NSEG, W) depends on m only -- the compact-row copy is cut along it -- while SG / RG follow the grid size.
 Plan make_plan(long long m, int rows_pad, int G) {
   Plan p;
   p.G = G;
-  int SG = 1;
   const long long cols128 = (m + 127) / 128;
-  for (int cand : {8, 4, 2, 1}) {
-    if (G % cand == 0 && cand <= std::max<long long>(1, cols128)) { SG = cand; break; }
-  }
+  int sgmax = 1;
+  for (int cand : {8, 4, 2, 1}) if (cand <= std::max<long long>(1, cols128)) { sgmax = cand; break; }
   const long long nseg_min = (m + kSegMax - 1) / kSegMax;
-  long long NSEG = SG * std::max<long long>(1, (nseg_min + SG - 1) / SG);
+  long long NSEG = sgmax * std::max<long long>(1, (nseg_min + sgmax - 1) / sgmax);
   long long W = round_up((m + NSEG - 1) / NSEG, 128);
   if (W < 128) W = 128;
-  NSEG = std::max<long long>(SG, round_up((m + W - 1) / W, SG));
+  NSEG = std::max<long long>(sgmax, round_up((m + W - 1) / W, sgmax));
+  int SG = 1;
+  for (int cand : {8, 4, 2, 1}) if (cand <= sgmax && G % cand == 0) { SG = cand; break; }
   p.SG = SG; p.RG = G / SG; p.NSEG = (int)NSEG; p.W = (int)W; p.NRT = rows_pad / kRowTile;
   return p;
 }
-
 
 // stripe decomposition: item enumeration, per-CTA runs, buffers (clp_dense2.cuh)
 int build_plan2(clp_handle h) {
@@ -254,8 +254,11 @@ int build_sparse(clp_handle h, bool force) {
   sparse_count_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
                                                         h->sp_ptr4.as<unsigned int>(), &sb->counts[0]);
   CLP_CUDA(h, cudaGetLastError());
-  unsigned long long* total4_d = reinterpret_cast<unsigned long long*>(&sb->leaf[0][0]);  // scratch word of the sync block
-  sparse_scan_kernel<<<1, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), nptr, total4_d);
+  unsigned long long* total4_d = reinterpret_cast<unsigned long long*>(&sb->leaf[0][0]);  // scratch words of the sync block
+  unsigned long long* segtot_d = reinterpret_cast<unsigned long long*>(&sb->leaf[1][0]);  // [<= 64] (leaf[1..4])
+  sparse_scan_seg_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad + 1, segtot_d);
+  CLP_CUDA(h, cudaGetLastError());
+  sparse_scan_fix_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad + 1, nseg, segtot_d, total4_d);
   CLP_CUDA(h, cudaGetLastError());
   unsigned long long host[3] = {0, 0, 0};
   CLP_CUDA(h, cudaMemcpyAsync(&host[0], total4_d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -282,11 +285,14 @@ int build_sparse(clp_handle h, bool force) {
 
 int set_plan_for(clp_handle h, int mode) {
   int ctas = h->ctas_for(mode);
-  if (mode == 3 && ctas == 3) {
-    // 3 CTAs/SM only pay off when every CTA still gets several 32-row tiles; measured at m=20000:
+  if (mode == 3) {
+    // more than 2 CTAs/SM only pay off when every CTA still gets several 32-row tiles; measured at m=20000:
     // 1 GPU (625 tiles) 3 > 2 CTAs/SM, 8 GPUs (79 tiles per shard) 2 > 3 > 1
-    const Plan p3 = make_plan(h->m, h->rows_pad, h->sm_count * 3);
-    if (p3.NRT < 4 * p3.RG) ctas = 2;
+    while (ctas > 2) {
+      const Plan pc = make_plan(h->m, h->rows_pad, h->sm_count * ctas);
+      if (pc.NRT >= 4 * pc.RG) break;
+      --ctas;
+    }
   }
   h->plan = make_plan(h->m, h->rows_pad, h->sm_count * ctas);
   CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
@@ -297,7 +303,8 @@ int set_plan_for(clp_handle h, int mode) {
 int finalize_matrix(clp_handle h) {
   int eff = h->dense_mode;
   if (eff == 3 || eff == 4) {
-    if (int rc = set_plan_for(h, 3)) return rc;  // the compact copy is cut along this plan's column segments
+    h->sp.plain = 0;
+    if (int rc = set_plan_for(h, 3)) return rc;  // column segmentation (NSEG, W) depends on m only
     const int rc = (h->storage == CLP_STORE_F64) ? build_sparse<double>(h, eff == 3) : build_sparse<float>(h, eff == 3);
     if (rc == CLP_OK) eff = 3;
     else if (rc == 1) eff = (h->world > 1) ? 0 : 2;
@@ -495,7 +502,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   a.prm.maxiniters = P.maxiniters; a.prm.maxoliters = P.maxoliters; a.prm.maxlsiters = P.maxlsiters;
   a.prm.rescale_u0 = P.rescale_u0 ? 1 : 0;
   SyncBlock* sb = h->sync.as<SyncBlock>();
-  a.bar.sb = sb; a.bar.nleaf = h->plan.SG; a.bar.leafsize = h->plan.RG;
+  a.bar.sb = sb; a.bar.nleaf = std::min(32, h->plan.G); a.bar.G = h->plan.G;
   a.u0 = h->u0dev.as<double>();
   a.vecs = h->vecs.as<double>();
   a.ll = h->llbuf.as<uint4>();
@@ -653,6 +660,7 @@ int clp_create(int device, int storage, clp_handle* out) {
   if (e != cudaSuccess || occ < 1 || occ3 < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
   h->ctas_per_sm = std::min(occ, 2);
   h->ctas_sparse = std::min(occ3, 3);
+
   *out = h;
   return CLP_OK;
 }

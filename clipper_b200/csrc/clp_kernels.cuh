@@ -81,7 +81,7 @@ template <> __device__ __forceinline__ double encode<double>(double mval, bool c
 // the others).  Every spin is bounded: a lost CTA / peer can never hang the GPU.
 // ------------------------------------------------------------------------------------------
 struct SyncBlock {  // zeroed by the host before every launch
-  unsigned long long leaf[8][16];  // arrival counters, one 128-byte line each
+  unsigned long long leaf[32][16]; // arrival counters, one 128-byte line each
   unsigned long long root[16];
   unsigned long long gen[16];      // generation published by the last arriver
   double bcast[2][kRedVals];       // globally reduced scalars of the current exchange
@@ -92,8 +92,8 @@ struct SyncBlock {  // zeroed by the host before every launch
 
 struct TreeBar {
   SyncBlock* sb;
-  int nleaf;     // == Plan::SG
-  int leafsize;  // == Plan::RG   (G = nleaf * leafsize)
+  int nleaf;     // <= 32 arrival counters; CTA b arrives at leaf b % nleaf
+  int G;         // CTAs in the grid (leaves differ in size by at most one)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -111,8 +111,10 @@ __device__ __forceinline__ bool bar_arrive(const TreeBar& b, unsigned long long 
   if (threadIdx.x == 0) {
     int last = 0;
     __threadfence();
-    unsigned long long old = atomicAdd(&b.sb->leaf[blockIdx.x % b.nleaf][0], 1ULL);
-    if (old + 1ULL == round * (unsigned long long)b.leafsize) {
+    const int leaf = blockIdx.x % b.nleaf;
+    const int leafsize = b.G / b.nleaf + (leaf < b.G % b.nleaf ? 1 : 0);
+    unsigned long long old = atomicAdd(&b.sb->leaf[leaf][0], 1ULL);
+    if (old + 1ULL == round * (unsigned long long)leafsize) {
       __threadfence();
       old = atomicAdd(&b.sb->root[0], 1ULL);
       if (old + 1ULL == round * (unsigned long long)b.nleaf) { last = 1; __threadfence(); }
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 matvec_sparse_partials_kernel(MatView mv, Plan p, StageArgs st, SparseView sp, double* partM, double* partC) {
   __shared__ __align__(16) double vs[kSegMax + 2];
   __shared__ double red_smem[kWarps];
-  sparse_phase<T>(mv, p, st, sp, partM, partC, vs, red_smem);
+  sparse_phase<T, false>(mv, p, st, sp, partM, partC, vs, red_smem);
 }
 
 // the same two steps for the stripe decomposition (clp_dense2.cuh)
@@ -860,7 +862,7 @@ __global__ void __launch_bounds__(kThreads, MODE == 3 ? 3 : 2) solver_kernel(Sol
   for (int lr = (blockIdx.x + p.G * (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31); lr < mv.rows; lr += p.G * kWarps * 32)
 #define CLP_DENSE_PASS()                                                                    \
   if constexpr (MODE == 0) matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem);      \
-  else if constexpr (MODE == 3) sparse_phase<T>(mv, p, st, a.sp, a.partM, a.partC, vs, red_smem); \
+  else if constexpr (MODE == 3) sparse_phase<T, false>(mv, p, st, a.sp, a.partM, a.partC, vs, red_smem); \
   else dense2_phase<T, MODE == 2>(mv, a.plan2, st, a.d2, vs);
 #define CLP_GATHER()                                                                        \
   if constexpr (MODE == 0 || MODE == 3) gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv); \

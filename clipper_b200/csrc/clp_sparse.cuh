@@ -69,24 +69,50 @@ __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, i
   }
 }
 
-// pass 2: exclusive scan of the n unit counts in place (single block; n <= 64 * 262145); total -> *total4
-__global__ void sparse_scan_kernel(unsigned int* cnt4, long long n, unsigned long long* total4) {
-  __shared__ unsigned long long part[1024];
-  const int t = threadIdx.x, nt = blockDim.x;
-  const long long per = (n + nt - 1) / nt;
-  const long long b = t * per, e = (b + per < n) ? b + per : n;
-  unsigned long long s = 0;
-  for (long long i = b; i < e; ++i) s += cnt4[i];
-  part[t] = s;
-  __syncthreads();
-  if (t == 0) {
-    unsigned long long run = 0;
-    for (int i = 0; i < nt; ++i) { const unsigned long long v = part[i]; part[i] = run; run += v; }
-    *total4 = run;
+// pass 2a: one block per column segment: exclusive scan (in place) of that segment's row counts, walking the
+// array in coalesced tiles of 1024; the segment total goes to segtot[seg]
+__global__ void sparse_scan_seg_kernel(unsigned int* cnt4, int n, unsigned long long* segtot) {
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned int carry_s;
+  unsigned int* a = cnt4 + (size_t)blockIdx.x * n;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  unsigned long long carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + t;
+    const unsigned int x = (i < n) ? a[i] : 0u;
+    unsigned int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      unsigned int v = wsum[lane], s = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      wsum[lane] = s - v;                 // exclusive prefix of the warp sums
+      if (lane == 31) carry_s = s;        // tile total
+    }
+    __syncthreads();
+    if (i < n) a[i] = (unsigned int)(carry + wsum[w] + (inc - x));
+    carry += carry_s;
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned long long run = part[t];
-  for (long long i = b; i < e; ++i) { const unsigned int c = cnt4[i]; cnt4[i] = (unsigned int)run; run += c; }
+  if (t == 0) segtot[blockIdx.x] = carry;
+}
+
+// pass 2b: add the start of each segment (prefix of the segment totals); block 0 also publishes the grand total
+__global__ void sparse_scan_fix_kernel(unsigned int* cnt4, int n, int nseg, const unsigned long long* segtot,
+                                       unsigned long long* total4) {
+  unsigned long long base = 0;
+  for (int s = 0; s < (int)blockIdx.x; ++s) base += segtot[s];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int s = 0; s < nseg; ++s) tot += segtot[s];
+    *total4 = tot;
+  }
+  if (base == 0) return;
+  unsigned int* a = cnt4 + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] += (unsigned int)base;
 }
 
 // pass 3: one warp per row writes the kept entries of each segment in column order, then the padding.
@@ -161,19 +187,13 @@ __device__ __forceinline__ double vs_at(const double* vs, unsigned int byte_off)
 // latency-bound, so the kernels that contain it run 3 CTAs per SM.
 // vs holds the segment of v in natural order, vs[kSegMax] == 0.
 template <typename T, bool PLAIN>
-__device__ __forceinline__ void sparse_rows4(const SparseView& sp, int lr, int seg, const double* vs,
+__device__ __forceinline__ void sparse_rows4(const SparseView& sp, const unsigned int (&a)[5], const double* vs,
                                              double (&acc)[8]) {
   const int lane = threadIdx.x & 31;
   const T* val = reinterpret_cast<const T*>(sp.val);
-  const unsigned int* pa = sp.ptr4 + (size_t)seg * (sp.rows_pad + 1) + lr;
   unsigned int beg[4], n4[4], nmax = 0;
-  {
-    unsigned int a[5];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) a[r] = pa[r];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { beg[r] = a[r]; n4[r] = a[r + 1] - a[r]; nmax = max(nmax, n4[r]); }
-  }
+  for (int r = 0; r < 4; ++r) { beg[r] = a[r]; n4[r] = a[r + 1] - a[r]; nmax = max(nmax, n4[r]); }
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0;
   for (unsigned int c = lane; c < nmax; c += 32) {
@@ -201,7 +221,9 @@ __device__ __forceinline__ void sparse_rows4(const SparseView& sp, int lr, int s
 
 // whole sparse pass of one CTA: same decomposition and partial layout as matvec_phase.
 // vs must hold kSegMax + 1 doubles.
-template <typename T>
+// (Tried: a plain-only instance capped at 64 registers for 4 CTAs/SM -- the sweep gained 4 %, the two
+// synchronisation steps of the evaluation lost it again with 592 CTAs; not kept.)
+template <typename T, bool PLAIN_ONLY>
 __device__ void sparse_phase(const MatView& mv, const Plan& p, const StageArgs& st, const SparseView& sp,
                              double* partM, double* partC, double* vs, double* red_smem) {
   const int sg = blockIdx.x % p.SG, rg = blockIdx.x / p.SG;
@@ -209,11 +231,25 @@ __device__ void sparse_phase(const MatView& mv, const Plan& p, const StageArgs& 
   if (threadIdx.x == 0) vs[kSegMax] = 0.0;
   for (int seg = sg; seg < p.NSEG; seg += p.SG) {
     stage_segment<double>(st, p, mv.m, seg, rg == 0, vs, red_smem);  // <double>: natural (unpermuted) order
+    // slice pointers of the next item are fetched while the current one is processed
+    const unsigned int* pseg = sp.ptr4 + (size_t)seg * (sp.rows_pad + 1) + warp * kRowsPerWarp;
+    unsigned int nxt[5] = {0u, 0u, 0u, 0u, 0u};
+    if (rg < p.NRT) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) nxt[r] = pseg[(size_t)rg * kRowTile + r];
+    }
     for (int rt = rg; rt < p.NRT; rt += p.RG) {
       const int lr = rt * kRowTile + warp * kRowsPerWarp;
+      unsigned int cur[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) cur[r] = nxt[r];
+      if (rt + p.RG < p.NRT) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) nxt[r] = pseg[(size_t)(rt + p.RG) * kRowTile + r];
+      }
       double acc[8];
-      if (sp.plain) sparse_rows4<T, true>(sp, lr, seg, vs, acc);
-      else sparse_rows4<T, false>(sp, lr, seg, vs, acc);
+      if (PLAIN_ONLY || sp.plain) sparse_rows4<T, true>(sp, cur, vs, acc);
+      else sparse_rows4<T, false>(sp, cur, vs, acc);
       const double tot = warp_reduce8(acc);
       if ((lane & 3) == 0) {
         const int qv = lane >> 2;  // 0..3: M of row qv, 4..7: C of row qv-4
