@@ -43,6 +43,11 @@ struct DevBuf {
 
 }  // namespace
 
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
 struct clp_handle_s {
   int device = 0;
   int storage = CLP_STORE_F32;
@@ -55,6 +60,8 @@ struct clp_handle_s {
   int ctas_per_sm = 2;       // dense sweeps (and the user cap set by clp_set_ctas_per_sm)
   int ctas_sparse = 3;       // compact-row sweep: latency-bound, few registers -> 3 CTAs per SM
   int ctas_cap = 3;          // user cap (clp_set_ctas_per_sm)
+  int head_kb = env_int("CLP_HEAD_KB", 0);       // compact sweep: KB per CTA prefetched into L2 during the sync steps
+  int head_where = env_int("CLP_HEAD_WHERE", 1);
   int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? ctas_sparse : ctas_per_sm); }
 
   // sharding (row block [row0,row0+rows) of the m x m matrix lives here)
@@ -100,7 +107,7 @@ struct clp_handle_s {
                           //            3 compact rows, 4 auto (compact rows when the graph is sparse enough, else 2 / 0)
   int dense_mode_eff = 2; // effective, decided when the matrix is finalised
   // compact-row copy (clp_sparse.cuh)
-  DevBuf sp_val, sp_col, sp_ptr4;
+  DevBuf sp_val, sp_col, sp_ptr4, sp_part, sp_item, sp_rowid, sp_rank;  // sp_ptr4: chunk counts per (segment, row)
   unsigned long long sp_nnz = 0, sp_nnz_real = 0;
   SparseView sp{};
   Plan2 plan2{};
@@ -254,11 +261,23 @@ int build_sparse(clp_handle h, bool force) {
   sparse_count_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
                                                         h->sp_ptr4.as<unsigned int>(), &sb->counts[0]);
   CLP_CUDA(h, cudaGetLastError());
+  // sort the rows of every segment by slice length, group them four at a time, scan the item lengths
+  const int NI = h->rows_pad / 4;
+  const long long nitem = (long long)nseg * (NI + 1);
+  CLP_CUDA(h, h->sp_rowid.ensure((size_t)nseg * h->rows_pad * sizeof(unsigned int)));
+  CLP_CUDA(h, h->sp_rank.ensure((size_t)nseg * h->rows_pad * sizeof(unsigned int)));
+  CLP_CUDA(h, h->sp_item.ensure((size_t)nitem * sizeof(unsigned int)));
+  sell_sort_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad, h->sp_rowid.as<unsigned int>(),
+                                                 h->sp_rank.as<unsigned int>());
+  CLP_CUDA(h, cudaGetLastError());
+  sell_itemlen_kernel<<<(unsigned)((nitem + 255) / 256), 256, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->sp_rowid.as<unsigned int>(),
+                                                                              h->rows_pad, nseg, h->sp_item.as<unsigned int>());
+  CLP_CUDA(h, cudaGetLastError());
   unsigned long long* total4_d = reinterpret_cast<unsigned long long*>(&sb->leaf[0][0]);  // scratch words of the sync block
   unsigned long long* segtot_d = reinterpret_cast<unsigned long long*>(&sb->leaf[1][0]);  // [<= 64] (leaf[1..4])
-  sparse_scan_seg_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad + 1, segtot_d);
+  sparse_scan_seg_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_item.as<unsigned int>(), NI + 1, segtot_d);
   CLP_CUDA(h, cudaGetLastError());
-  sparse_scan_fix_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad + 1, nseg, segtot_d, total4_d);
+  sparse_scan_fix_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_item.as<unsigned int>(), NI + 1, nseg, segtot_d, total4_d);
   CLP_CUDA(h, cudaGetLastError());
   unsigned long long host[3] = {0, 0, 0};
   CLP_CUDA(h, cudaMemcpyAsync(&host[0], total4_d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -266,7 +285,7 @@ int build_sparse(clp_handle h, bool force) {
   CLP_CUDA(h, cudaStreamSynchronize(h->stream));
   const unsigned long long n4 = host[0];
   if (n4 >= 0xffffffffull) { if (force) return fail(h, CLP_ERR_UNSUPPORTED, "compact rows: too many entries"); return 1; }
-  h->sp_nnz = 4 * n4;        // stored entries (slices padded to multiples of 4): what one pass reads
+  h->sp_nnz = 4 * n4;        // stored entries (incl. the padding of slices and items): what one pass reads
   h->sp_nnz_real = host[1];  // non-neutral entries of the local rows
   h->sp.plain = host[2] == 0 ? 1 : 0;
   // worth it?  compare with the bytes of the best dense sweep (upper triangle two-sided on one GPU, full rows when sharded)
@@ -276,10 +295,22 @@ int build_sparse(clp_handle h, bool force) {
   CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(T)));
   CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(unsigned short)));
   sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
-                                                       h->sp_ptr4.as<unsigned int>(), h->sp_val.as<T>(), h->sp_col.as<unsigned short>());
+                                                       h->sp_item.as<unsigned int>(), h->sp_rank.as<unsigned int>(),
+                                                       h->sp_val.as<T>(), h->sp_col.as<unsigned short>(),
+                                                       std::getenv("CLP_PROBE_NO_CONFLICT") ? 1 : 0);
   CLP_CUDA(h, cudaGetLastError());
   h->sp.val = h->sp_val.p; h->sp.off16 = h->sp_col.as<unsigned short>();
-  h->sp.ptr4 = h->sp_ptr4.as<unsigned int>(); h->sp.rows_pad = h->rows_pad;
+  h->sp.itemptr = h->sp_item.as<unsigned int>(); h->sp.rowid = h->sp_rowid.as<unsigned int>(); h->sp.rows_pad = h->rows_pad;
+  // byte-balanced contiguous item range of every CTA (depends on the grid size: rebuilt with the plan)
+  CLP_CUDA(h, h->sp_part.ensure(2 * ((size_t)p.G + 1) * sizeof(unsigned int)));
+  sparse_partition_kernel<<<(p.G + 1 + 255) / 256, 256, 0, h->stream>>>(h->sp.itemptr, h->rows_pad, nseg, p.G, h->sp_part.as<unsigned int>(),
+                                                                        h->sp_part.as<unsigned int>() + p.G + 1);
+  CLP_CUDA(h, cudaGetLastError());
+  h->sp.cta_first = h->sp_part.as<unsigned int>();
+  h->sp.cta_chunk = h->sp.cta_first + p.G + 1;
+  // head of every CTA's range kept warm in L2 across the synchronisation steps: 24 B per chunk (fp32)
+  h->sp.head_chunks = (unsigned int)(std::max(0, h->head_kb) * 1024 / (4 * ((int)sizeof(T) + 2)) / 256 * 256);
+  h->sp.head_where = h->head_where;
   return CLP_OK;
 }
 
@@ -1036,7 +1067,7 @@ int clp_sparse_info(clp_handle h, int64_t* nnz_kept, int64_t* bytes_per_pass) {
   if (!h) return CLP_ERR_INVALID;
   if (nnz_kept) *nnz_kept = (int64_t)h->sp_nnz_real;
   if (bytes_per_pass)
-    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) + (unsigned long long)(h->rows + 1) * h->plan.NSEG * 4);
+    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) + (unsigned long long)(h->rows_pad / 4) * h->plan.NSEG * 20);
   return CLP_OK;
 }
 

@@ -1,34 +1,51 @@
-// clp_sparse.cuh -- compact-row copy of the affinity matrix and its sweep.
+// clp_sparse.cuh -- compact copy of the affinity matrix and its sweep.
 //
 // The consistency graph is sparse (14.9 % at BASELINE.json's config 2), so after the dense build the
-// non-neutral entries (everything except the -0.0 "inconsistent" code) of every local row are compacted,
-// in column order, into
+// non-neutral entries (everything except the -0.0 "inconsistent" code) of every local row are compacted into
 //      val[]  : the stored element itself (fp32 / fp64; sign bit = constraint bit, as in the dense store)
 //      off16[]: 8 * (column - first column of its segment) -- the byte offset of v[column] inside the
 //               shared-memory copy of the segment (segments are <= 4096 columns wide)
 // = 6 bytes per kept entry (fp32 storage) instead of 4 bytes per matrix element.
-// Layout is SEGMENT-major: all row slices of column segment 0, then segment 1, ...; inside a segment the
-// slices of consecutive rows are adjacent, so the 32 rows x 1 segment a CTA works on are one contiguous
-// range of HBM.  Every slice is padded to a multiple of 4 entries (16-byte value loads); padding entries
-// point at a zero slot behind the staged segment.  slice(row, seg) in units of 4 entries:
-//      [ ptr4[seg * (rows_pad + 1) + row] , ptr4[seg * (rows_pad + 1) + row + 1] )
-// The sweep keeps the first-generation decomposition (segments of v staged in shared memory, 32-row tiles,
-// per-segment partial products, fixed-order combine); only the inner row sweep changes.
+//
+// Layout (a sliced-ELL variant: SELL-4 with the sort window = one whole column segment):
+//  * the columns are cut into the NSEG segments of the Plan; a "slice" is one row x one segment, stored in
+//    CHUNKS of 4 entries (16-byte value load + 8-byte offset load); the last chunk is padded with neutral
+//    entries that point at a zero slot behind the staged segment;
+//  * inside a segment the rows are SORTED by slice length (descending) and taken four at a time: an ITEM.
+//    The four slices of an item are padded to the longest of them (neighbours in sorted order: < 1 % padding)
+//    and interleaved chunk by chunk: chunk k of member s sits at chunk position 4 k + s of the item.
+//    An item is therefore ONE contiguous run of HBM that a warp streams with perfectly coalesced loads
+//    (lane l reads chunks l, l+32, ... -> always member l & 3), each lane keeps just two accumulators, and
+//    the row sums need a 3-step butterfly over the 8 lanes of a member instead of the 18 shuffles of the
+//    row-major variant; the registers saved buy a deeper unroll (more bytes in flight per warp).
+//  * items of segment 0, then segment 1, ...: one stream, itemptr[seg][i] = first chunk of item i
+//    (cumulative over everything before it), rowid[seg][4 i + s] = local row of member s.
+// Row densities differ a lot (config 2: 93 +- 24 chunks per slice), which is why the rows are sorted and why
+// the sweep is split by bytes, not by row count (sparse_partition_kernel).
+// The sum of a row does not depend on which item it landed in nor on the (atomic, unordered) tie-breaking of
+// the sort: its chunks k go to accumulator lane k mod 8 in increasing k, then the fixed butterfly.
 // "plain" matrices (every kept entry has M > 0 and C = 1 -- always true after scorePairwiseConsistency) take
 // a shorter path: Chat v is then just the sum of the gathered v.
-// Algorithmic bytes per objective evaluation: 6 * stored entries + 4 * NSEG * (rows + 1).
+// Algorithmic bytes per objective evaluation: 6 * stored entries + 20 * NSEG * rows / 4.
 #pragma once
 
 namespace clp {
 
 constexpr unsigned int kZeroSlot = kSegMax * 8;  // byte offset of the zero element behind the staged segment
+constexpr int kSellUnroll = 3;                   // chunks per lane and round; two rounds are in flight
+constexpr unsigned int kItemCost = 16;           // fixed cost of an item (pointer fetch, reduction, store) in chunks
 
 struct SparseView {
-  const void* val;             // T [4 * n4]
-  const unsigned short* off16; // [4 * n4]
-  const unsigned int* ptr4;    // [NSEG][rows_pad + 1]
+  const void* val;               // T [4 * chunks]
+  const unsigned short* off16;   // [4 * chunks]
+  const unsigned int* itemptr;   // [NSEG][NI + 1], NI = rows_pad / 4
+  const unsigned int* rowid;     // [NSEG][rows_pad]
   int rows_pad;
-  int plain;                   // every kept entry has M > 0 and C = 1
+  int plain;                     // every kept entry has M > 0 and C = 1
+  const unsigned int* cta_first; // [G + 1] first item of every CTA (balanced by bytes), see sparse_partition_kernel
+  const unsigned int* cta_chunk; // [G + 1] first chunk of every CTA's range
+  unsigned int head_chunks;      // chunks at the head of its range a CTA asks L2 to fetch while it waits (0: off)
+  int head_where;                // 1: before the wait that ends the combine step, 2: also before the one that ends the sweep
 };
 
 template <typename T> __device__ __forceinline__ bool is_neutral(T s);
@@ -69,7 +86,43 @@ __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, i
   }
 }
 
-// pass 2a: one block per column segment: exclusive scan (in place) of that segment's row counts, walking the
+// pass 2: one block per column segment sorts the rows by slice length, longest first (counting sort over the
+// <= 1025 possible lengths; ties in arrival order, which does not influence any result).
+//   rowid[seg][pos] = row at sorted position pos, rank[seg][row] = its position
+__global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, unsigned int* rowid, unsigned int* rank) {
+  __shared__ unsigned int hist[kSegMax / 4 + 2];
+  const int nb = kSegMax / 4 + 1;
+  const unsigned int* c = cnt4 + (size_t)blockIdx.x * (rows_pad + 1);
+  for (int i = threadIdx.x; i <= nb; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) atomicAdd(&hist[min(c[r], (unsigned int)(nb - 1))], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // start of every length class, longest class first
+    unsigned int run = 0;
+    for (int b = nb - 1; b >= 0; --b) { const unsigned int h = hist[b]; hist[b] = run; run += h; }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) {
+    const unsigned int pos = atomicAdd(&hist[min(c[r], (unsigned int)(nb - 1))], 1u);
+    rowid[(size_t)blockIdx.x * rows_pad + pos] = (unsigned int)r;
+    rank[(size_t)blockIdx.x * rows_pad + r] = pos;
+  }
+}
+
+// pass 3: chunks of every item = 4 x its longest member (the first one in sorted order); scanned in place by
+// the two scan kernels below into itemptr[seg][0..NI]
+__global__ void sell_itemlen_kernel(const unsigned int* cnt4, const unsigned int* rowid, int rows_pad, int nseg,
+                                    unsigned int* itemptr) {
+  const int NI = rows_pad >> 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nseg * (NI + 1)) return;
+  const int seg = (int)(t / (NI + 1)), i = (int)(t - (long long)seg * (NI + 1));
+  unsigned int len = 0u;
+  if (i < NI) len = 4u * cnt4[(size_t)seg * (rows_pad + 1) + rowid[(size_t)seg * rows_pad + 4 * i]];
+  itemptr[t] = len;
+}
+
+// pass 3a: one block per column segment: exclusive scan (in place) of that segment's item lengths, walking the
 // array in coalesced tiles of 1024; the segment total goes to segtot[seg]
 __global__ void sparse_scan_seg_kernel(unsigned int* cnt4, int n, unsigned long long* segtot) {
   __shared__ unsigned int wsum[32];
@@ -100,7 +153,7 @@ __global__ void sparse_scan_seg_kernel(unsigned int* cnt4, int n, unsigned long 
   if (t == 0) segtot[blockIdx.x] = carry;
 }
 
-// pass 2b: add the start of each segment (prefix of the segment totals); block 0 also publishes the grand total
+// pass 3b: add the start of each segment (prefix of the segment totals); block 0 also publishes the grand total
 __global__ void sparse_scan_fix_kernel(unsigned int* cnt4, int n, int nseg, const unsigned long long* segtot,
                                        unsigned long long* total4) {
   unsigned long long base = 0;
@@ -115,42 +168,57 @@ __global__ void sparse_scan_fix_kernel(unsigned int* cnt4, int n, int nseg, cons
   for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] += (unsigned int)base;
 }
 
-// pass 3: one warp per row writes the kept entries of each segment in column order, then the padding.
-// ptr4 is the scanned array; the slot [seg][rows_pad] of every segment holds the start of the next one.
+// pass 4: one warp per (padded) local row writes its kept entries, in column order, into its member lane of
+// its item in every segment, then the padding up to the item's length.
 template <typename T>
 __global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
-                                   const unsigned int* ptr4, T* val, unsigned short* off16) {
+                                   const unsigned int* itemptr, const unsigned int* rank, T* val, unsigned short* off16,
+                                   int probe_no_conflict) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  if (warp >= rows_pad) return;
+  const int NI = rows_pad >> 2;
   for (int s = 0; s < nseg; ++s) {
-    const unsigned int* pp = ptr4 + (size_t)s * (rows_pad + 1) + warp;
-    unsigned long long pos = 4ull * pp[0];
-    const unsigned long long slice_end = 4ull * pp[1];
-    const int c0 = s * W, c1 = min(m, c0 + W);
-    for (int j0 = c0; j0 < c1; j0 += 128) {
-      const int j = j0 + lane * 4;
-      T x[4];
-      unsigned int keep = 0;
+    const unsigned int pos = rank[(size_t)s * rows_pad + warp];
+    const unsigned int* ip = itemptr + (size_t)s * (NI + 1) + (pos >> 2);
+    const unsigned long long base = 4ull * ip[0] + 4ull * (pos & 3u);  // entry index of (chunk 0, member pos & 3)
+    const unsigned int cap = ip[1] - ip[0];                              // entries this member may hold (4 x chunks / 4)
+    // entry w of the slice lives at base + 16 * (w / 4) + (w % 4)
+    unsigned int n = 0;
+    if (warp < rows) {
+      const int c0 = s * W, c1 = min(m, c0 + W);
+      for (int j0 = c0; j0 < c1; j0 += 128) {
+        const int j = j0 + lane * 4;
+        T x[4];
+        unsigned int keep = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        x[e] = (j + e < c1) ? M[(size_t)warp * ld + j + e] : encode<T>(0.0, false);
-        keep |= (!is_neutral<T>(x[e]) ? 1u : 0u) << e;
+        for (int e = 0; e < 4; ++e) {
+          x[e] = (j + e < c1) ? M[(size_t)warp * ld + j + e] : encode<T>(0.0, false);
+          keep |= (!is_neutral<T>(x[e]) ? 1u : 0u) << e;
+        }
+        const unsigned int cnt = __popc(keep);
+        unsigned int pre = cnt;  // inclusive scan over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int y = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += y;
+        }
+        const unsigned int total = __shfl_sync(0xffffffffu, pre, 31);
+        unsigned int w = n + (pre - cnt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (keep & (1u << e)) {
+            const unsigned long long at = base + 16ull * (w >> 2) + (w & 3u);
+            val[at] = x[e]; off16[at] = (unsigned short)(8 * (j + e - c0)); ++w;
+            // timing probe only (wrong results): every half-warp of the sweep reads 16 distinct banks
+            if (probe_no_conflict) off16[at] = (unsigned short)(8 * (((at >> 2) - ip[0]) & 15u));
+          }
+        n += total;
       }
-      const unsigned int cnt = __popc(keep);
-      unsigned int pre = cnt;  // inclusive scan over lanes
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int y = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += y;
-      }
-      const unsigned int total = __shfl_sync(0xffffffffu, pre, 31);
-      unsigned long long w = pos + (pre - cnt);
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (keep & (1u << e)) { val[w] = x[e]; off16[w] = (unsigned short)(8 * (j + e - c0)); ++w; }
-      pos += total;
     }
-    for (unsigned long long w = pos + lane; w < slice_end; w += 32) { val[w] = encode<T>(0.0, false); off16[w] = (unsigned short)kZeroSlot; }
+    for (unsigned int w = n + lane; w < cap; w += 32) {
+      const unsigned long long at = base + 16ull * (w >> 2) + (w & 3u);
+      val[at] = encode<T>(0.0, false); off16[at] = (unsigned short)kZeroSlot;
+    }
   }
 }
 
@@ -182,82 +250,174 @@ __device__ __forceinline__ double vs_at(const double* vs, unsigned int byte_off)
   return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(vs) + byte_off);
 }
 
-// rows [lr, lr+4) x the staged segment.  The four row slices are walked together; every lane takes chunks of
-// 4 consecutive entries (4 x (16 + 8) bytes per lane in flight).  Few registers on purpose: the sweep is
-// latency-bound, so the kernels that contain it run 3 CTAs per SM.
+// A ROUND is kSellUnroll * 32 consecutive chunks of an item: lane l takes chunks l, l + 32, ... of the round
+// (always member l & 3 of the item because items start at a multiple of 4).
 // vs holds the segment of v in natural order, vs[kSegMax] == 0.
-template <typename T, bool PLAIN>
-__device__ __forceinline__ void sparse_rows4(const SparseView& sp, const unsigned int (&a)[5], const double* vs,
-                                             double (&acc)[8]) {
-  const int lane = threadIdx.x & 31;
+template <typename T>
+__device__ __forceinline__ void sell_load_round(const SparseView& sp, Entry4<T> (&E)[kSellUnroll], unsigned int j, unsigned int e) {
   const T* val = reinterpret_cast<const T*>(sp.val);
-  unsigned int beg[4], n4[4], nmax = 0;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) { beg[r] = a[r]; n4[r] = a[r + 1] - a[r]; nmax = max(nmax, n4[r]); }
+  for (int u = 0; u < kSellUnroll; ++u) {
+    if (j + 32u * u < e) E[u].load(val, sp.off16, 4ull * (j + 32u * u));
+    else E[u].neutral();
+  }
+}
+// aM/aC: this lane's share of its member's |M| v and C v (two interleaved accumulators each)
+template <typename T, bool PLAIN>
+__device__ __forceinline__ void sell_apply_round(const Entry4<T> (&E)[kSellUnroll], const double* vs, double (&aM)[2], double (&aC)[2]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-  for (unsigned int c = lane; c < nmax; c += 32) {
-    Entry4<T> E[4];
+  for (int u = 0; u < kSellUnroll; ++u)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (c < n4[r]) E[r].load(val, sp.off16, 4ull * (beg[r] + c));
-      else E[r].neutral();
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double v = vs_at(vs, off_of(E[r].k, e));
-        if (PLAIN) {
-          acc[r] = fma((double)E[r].get(e), v, acc[r]);  // padding: -0.0 * 0.0
-          acc[4 + r] += v;
-        } else {
-          double dummyM = 0.0, dummyC = 0.0;
-          apply_elem<false>(E[r].get(e), v, 0.0, acc[r], acc[4 + r], dummyM, dummyC);
-        }
+    for (int q = 0; q < 4; ++q) {
+      const double v = vs_at(vs, off_of(E[u].k, q));
+      if (PLAIN) {
+        aM[u & 1] = fma((double)E[u].get(q), v, aM[u & 1]);  // padding: -0.0 * 0.0
+        aC[u & 1] += v;
+      } else {
+        double dummyM = 0.0, dummyC = 0.0;
+        apply_elem<false>(E[u].get(q), v, 0.0, aM[u & 1], aC[u & 1], dummyM, dummyC);
       }
+    }
+}
+
+// Work split of one sweep: every CTA gets a CONTIGUOUS range of the item stream holding 1/G of the cost
+// (chunks + kItemCost per item), found by bisection on itemptr; inside a CTA the warps draw items from a
+// shared-memory counter.  (Dealing 32-row tiles round-robin, as the dense sweep does, left the slowest CTA
+// with 1.23x the mean bytes at config 2.)
+__device__ __forceinline__ unsigned long long sparse_item_cost(const unsigned int* itemptr, int NI, int nseg, unsigned int g) {
+  const unsigned int seg = g / (unsigned int)NI, it = g - seg * (unsigned int)NI;
+  const unsigned int at = (seg >= (unsigned int)nseg) ? itemptr[(size_t)(nseg - 1) * (NI + 1) + NI]
+                                                      : itemptr[(size_t)seg * (NI + 1) + it];
+  return (unsigned long long)at + (unsigned long long)kItemCost * g;
+}
+
+__global__ void sparse_partition_kernel(const unsigned int* itemptr, int rows_pad, int nseg, int G, unsigned int* cta_first,
+                                        unsigned int* cta_chunk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > G) return;
+  const int NI = rows_pad >> 2;
+  const unsigned int N = (unsigned int)nseg * (unsigned int)NI;
+  const unsigned long long total = sparse_item_cost(itemptr, NI, nseg, N);
+  const unsigned long long target = total * (unsigned long long)b / (unsigned long long)G;  // total < 2^34, b <= 444
+  unsigned int lo = 0, hi = N;  // smallest g with cost(g) >= target
+  while (lo < hi) {
+    const unsigned int mid = lo + ((hi - lo) >> 1);
+    if (sparse_item_cost(itemptr, NI, nseg, mid) >= target) hi = mid; else lo = mid + 1;
+  }
+  if (b == G) lo = N;
+  cta_first[b] = lo;
+  cta_chunk[b] = (unsigned int)(sparse_item_cost(itemptr, NI, nseg, lo) - (unsigned long long)kItemCost * lo);
+}
+
+// asks L2 to fetch [p, p + bytes) -- p 16-byte aligned, bytes a non-zero multiple of 16
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned int bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
+// Called by every CTA right before it waits on a device-wide barrier of the solver: HBM is idle during the
+// synchronisation and combine steps of an evaluation (about 17 of 100 us at config 2), so the head of the range
+// this CTA will stream in the NEXT sweep -- the matrix does not depend on the line-search decision -- is pulled
+// into the 126 MB L2 meanwhile; the sweep then starts from L2 while HBM works on the rest.
+template <typename T>
+__device__ __forceinline__ void sparse_prefetch_head(const SparseView& sp) {
+  if (sp.head_chunks == 0u) return;
+  constexpr unsigned int kPiece = 256;  // chunks per request: 4 KB of fp32 values + 2 KB of offsets
+  const unsigned int c0 = sp.cta_chunk[blockIdx.x];
+  const unsigned int c1 = min(sp.cta_chunk[blockIdx.x + 1], c0 + sp.head_chunks);
+  const unsigned int c = c0 + kPiece * threadIdx.x;
+  if (c < c1) {
+    const unsigned int n = min(kPiece, c1 - c);  // multiple of 4
+    l2_prefetch(reinterpret_cast<const T*>(sp.val) + 4ull * c, n * 4u * (unsigned int)sizeof(T));
+    l2_prefetch(sp.off16 + 4ull * c, n * 8u);
   }
 }
 
-// whole sparse pass of one CTA: same decomposition and partial layout as matvec_phase.
+// whole sparse pass of one CTA: same partial layout as matvec_phase (partM/partC [NSEG][rows_pad]).
 // vs must hold kSegMax + 1 doubles.
-// (Tried: a plain-only instance capped at 64 registers for 4 CTAs/SM -- the sweep gained 4 %, the two
-// synchronisation steps of the evaluation lost it again with 592 CTAs; not kept.)
+// (Tried and dropped: a plain-only instance capped at 64 registers for 4 CTAs/SM -- the sweep gained 4 %, the
+// two synchronisation steps of the evaluation lost it again with 592 CTAs; a bulk L2 prefetch of the next
+// item (cp.async.bulk.prefetch.L2) -- 5 % slower.)
 template <typename T, bool PLAIN_ONLY>
 __device__ void sparse_phase(const MatView& mv, const Plan& p, const StageArgs& st, const SparseView& sp,
                              double* partM, double* partC, double* vs, double* red_smem) {
-  const int sg = blockIdx.x % p.SG, rg = blockIdx.x / p.SG;
+  __shared__ int next_item;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NI = sp.rows_pad >> 2;
+  unsigned int g = sp.cta_first[blockIdx.x];
+  const unsigned int gend = sp.cta_first[blockIdx.x + 1];
   if (threadIdx.x == 0) vs[kSegMax] = 0.0;
-  for (int seg = sg; seg < p.NSEG; seg += p.SG) {
-    stage_segment<double>(st, p, mv.m, seg, rg == 0, vs, red_smem);  // <double>: natural (unpermuted) order
-    // slice pointers of the next item are fetched while the current one is processed
-    const unsigned int* pseg = sp.ptr4 + (size_t)seg * (sp.rows_pad + 1) + warp * kRowsPerWarp;
-    unsigned int nxt[5] = {0u, 0u, 0u, 0u, 0u};
-    if (rg < p.NRT) {
+  for (int seg = (int)(g / (unsigned int)NI); g < gend; ++seg) {
+    const int it0 = (int)(g - (unsigned int)seg * NI);
+    const int it1 = (int)min(gend - (unsigned int)seg * NI, (unsigned int)NI);
+    if (threadIdx.x == 0) next_item = it0 + kWarps;
+    // the CTA that holds the first item of a segment publishes the staged vector and its sum
+    stage_segment<double>(st, p, mv.m, seg, it0 == 0, vs, red_smem);  // <double>: natural (unpermuted) order
+    const unsigned int* ipseg = sp.itemptr + (size_t)seg * (NI + 1);
+    const unsigned int* rowseg = sp.rowid + (size_t)seg * sp.rows_pad;
+    // lanes 0,1: chunk range of the item; lanes 2..5: its member rows
+    auto fetch = [&](int it) -> unsigned int {
+      if (it >= it1) return 0u;
+      if (lane < 2) return ipseg[it + lane];
+      if (lane < 6) return rowseg[4 * it + lane - 2];
+      return 0u;
+    };
+    // The warp walks its items as one stream of rounds, software-pipelined: the loads of the NEXT round -- the
+    // first round of the next item when the current one ends -- are issued before the current round is applied,
+    // so a warp always has a round in flight (a sweep that loads, waits, then computes leaves HBM idle while
+    // the 24 warps of an SM work through their 7-way bank-conflicted gathers).
+    int it = it0 + warp;
+    if (it < it1) {
+      unsigned int q0 = fetch(it);
+      int itn = 0;
+      if (lane == 0) itn = atomicAdd(&next_item, 1);
+      itn = __shfl_sync(0xffffffffu, itn, 0);
+      unsigned int q1 = fetch(itn);
+      unsigned int e = __shfl_sync(0xffffffffu, q0, 1), row = __shfl_sync(0xffffffffu, q0, 2 + (lane & 3));
+      unsigned int j = __shfl_sync(0xffffffffu, q0, 0) + lane;  // this lane's first chunk of the current round
+      double aM[2] = {0.0, 0.0}, aC[2] = {0.0, 0.0};
+      Entry4<T> A[kSellUnroll], B[kSellUnroll];
+      sell_load_round<T>(sp, A, j, e);
+      // applies round X of the current item after issuing the loads of the following round into Y;
+      // returns true when the warp has run out of items
+      auto step = [&](Entry4<T> (&X)[kSellUnroll], Entry4<T> (&Y)[kSellUnroll]) -> bool {
+        const bool last = (j - lane) + 32u * kSellUnroll >= e;  // warp-uniform
+        unsigned int jn = j + 32u * kSellUnroll, en = e, rown = row;
+        if (last) {
+          jn = __shfl_sync(0xffffffffu, q1, 0) + lane; en = __shfl_sync(0xffffffffu, q1, 1);
+          rown = __shfl_sync(0xffffffffu, q1, 2 + (lane & 3));
+          if (itn >= it1) en = jn - lane;  // no next item: nothing to load
+        }
+        sell_load_round<T>(sp, Y, jn, en);
+        if (PLAIN_ONLY || sp.plain) sell_apply_round<T, true>(X, vs, aM, aC);
+        else sell_apply_round<T, false>(X, vs, aM, aC);
+        if (last) {
+          double accM = aM[0] + aM[1], accC = aC[0] + aC[1];
 #pragma unroll
-      for (int r = 0; r < 5; ++r) nxt[r] = pseg[(size_t)rg * kRowTile + r];
-    }
-    for (int rt = rg; rt < p.NRT; rt += p.RG) {
-      const int lr = rt * kRowTile + warp * kRowsPerWarp;
-      unsigned int cur[5];
-#pragma unroll
-      for (int r = 0; r < 5; ++r) cur[r] = nxt[r];
-      if (rt + p.RG < p.NRT) {
-#pragma unroll
-        for (int r = 0; r < 5; ++r) nxt[r] = pseg[(size_t)(rt + p.RG) * kRowTile + r];
+          for (int o = 4; o < 32; o <<= 1) {
+            accM += __shfl_xor_sync(0xffffffffu, accM, o);
+            accC += __shfl_xor_sync(0xffffffffu, accC, o);
+          }
+          if (lane < 4) {
+            partM[(size_t)seg * mv.rows_pad + row] = accM;
+            partC[(size_t)seg * mv.rows_pad + row] = accC;
+          }
+          if (itn >= it1) return true;
+          aM[0] = aM[1] = aC[0] = aC[1] = 0.0;
+          it = itn;
+          if (lane == 0) itn = atomicAdd(&next_item, 1);
+          itn = __shfl_sync(0xffffffffu, itn, 0);
+          q1 = fetch(itn);
+        }
+        j = jn; e = en; row = rown;
+        return false;
+      };
+      for (;;) {
+        if (step(A, B)) break;
+        if (step(B, A)) break;
       }
-      double acc[8];
-      if (PLAIN_ONLY || sp.plain) sparse_rows4<T, true>(sp, cur, vs, acc);
-      else sparse_rows4<T, false>(sp, cur, vs, acc);
-      const double tot = warp_reduce8(acc);
-      if ((lane & 3) == 0) {
-        const int qv = lane >> 2;  // 0..3: M of row qv, 4..7: C of row qv-4
-        double* dst = (qv >> 2) ? partC : partM;
-        dst[(size_t)seg * mv.rows_pad + lr + (qv & 3)] = tot;
-      }
     }
-    __syncthreads();  // vs is re-staged by the next segment pass
+    __syncthreads();  // vs and next_item are re-used by the next segment pass
+    g = (unsigned int)(seg + 1) * NI;
   }
 }
 
