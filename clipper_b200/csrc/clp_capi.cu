@@ -85,7 +85,8 @@ struct clp_handle_s {
   bool A_host_valid = false;
   std::vector<int32_t> A_host;  // column-major m x 2
   DevBuf A_dev;                 // int32 [2m]
-  DevBuf E1, E2, D1dev, D2dev;
+  DevBuf E1, E2, D1dev, D2dev, F12;  // F12: fp32 positions of both endpoints (screening pass of the scoring kernel)
+  int score_filter = env_int("CLP_SCORE_FILTER", 1);
 
   // solver workspace
   DevBuf vecs;    // V_SLOTS x mpad doubles: U0 U1 MV0 MV1 CV0 CV1 (local only)
@@ -400,10 +401,17 @@ int read_sync(clp_handle h, SyncBlock* sb) {
 template <typename T, bool MIRROR>
 int launch_score_m(clp_handle h, int kind, int d, const ScoreArgs& a) {
   dim3 grid((unsigned)(h->ld / 128), (unsigned)(h->rows_pad / kRowTile));
-  if (kind == 1) score_tile_kernel<T, 1, 6, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
-  else if (d == 3) score_tile_kernel<T, 0, 3, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
-  else if (d == 2) score_tile_kernel<T, 0, 2, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
-  else score_tile_kernel<T, 0, 0, MIRROR><<<grid, kThreads, 0, h->stream>>>(a);
+  if (h->score_filter) {
+    if (kind == 1) score_tile_kernel<T, 1, 6, MIRROR, true><<<grid, kThreads, 0, h->stream>>>(a);
+    else if (d == 3) score_tile_kernel<T, 0, 3, MIRROR, true><<<grid, kThreads, 0, h->stream>>>(a);
+    else if (d == 2) score_tile_kernel<T, 0, 2, MIRROR, true><<<grid, kThreads, 0, h->stream>>>(a);
+    else score_tile_kernel<T, 0, 0, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
+  } else {
+    if (kind == 1) score_tile_kernel<T, 1, 6, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
+    else if (d == 3) score_tile_kernel<T, 0, 3, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
+    else if (d == 2) score_tile_kernel<T, 0, 2, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
+    else score_tile_kernel<T, 0, 0, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
+  }
   CLP_CUDA(h, cudaGetLastError());
   return CLP_OK;
 }
@@ -419,16 +427,19 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   if (int rc = ensure_matrix(h, m)) return rc;
   CLP_CUDA(h, h->E1.ensure((size_t)m * d * sizeof(double)));
   CLP_CUDA(h, h->E2.ensure((size_t)m * d * sizeof(double)));
+  CLP_CUDA(h, h->F12.ensure((size_t)2 * m * sizeof(float4)));
   if (int rc = reset_sync(h)) return rc;
   SyncBlock* sb = h->sync.as<SyncBlock>();
   const int tb = 256;
   gather_endpoints_kernel<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(
-      D1d, D2d, Ad, Ad + m, (int)m, d, n1, n2, h->E1.as<double>(), h->E2.as<double>(), &sb->error);
+      D1d, D2d, Ad, Ad + m, (int)m, d, n1, n2, h->E1.as<double>(), h->E2.as<double>(), h->F12.as<float4>(),
+      h->F12.as<float4>() + m, &sb->scale_bits, &sb->error);
   CLP_CUDA(h, cudaGetLastError());
   ScoreArgs a;
   a.E1 = h->E1.as<double>(); a.E2 = h->E2.as<double>();
   a.A0 = Ad; a.A1 = Ad + m;
   a.M = h->Mbuf.p; a.ld = h->ld; a.m = (int)m; a.row0 = h->row0; a.rows = h->rows; a.rows_pad = h->rows_pad;
+  a.F1 = h->F12.as<float4>(); a.F2 = a.F1 + m; a.scale_bits = &sb->scale_bits;
   a.d = d; a.p0 = p0; a.p1 = p1; a.p2 = p2; a.p3 = p3; a.affinityeps = h->prm.affinityeps;
   int rc = (h->storage == CLP_STORE_F64) ? launch_score<double>(h, kind, d, a) : launch_score<float>(h, kind, d, a);
   if (rc) return rc;
@@ -702,7 +713,7 @@ int clp_destroy(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r)
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
-  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->parts, &h->small,
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->F12, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->parts, &h->small,
                     &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);

@@ -88,6 +88,8 @@ struct SyncBlock {  // zeroed by the host before every launch
   int error;                       // 1: barrier / peer time-out, 2: bad association index
   int flags;                       // input-contract violations found by the encode kernels
   unsigned long long counts[2];
+  unsigned int scale_bits;         // scoring: float bits of max |position coordinate| (gather_endpoints_kernel)
+  unsigned int pad_;
 };
 
 struct TreeBar {
@@ -187,6 +189,10 @@ struct ScoreArgs {
   int d;             // runtime dimension (generic path)
   double p0, p1, p2, p3;  // sigma,epsilon,mindist | sigp,epsp,sign,epsn
   double affinityeps;
+  // fp32 screening (FILTER instances): positions of both endpoints as float4 and the largest |coordinate|
+  const float4* F1;  // [m] (x, y, z, 0) of E1
+  const float4* F2;  // [m]
+  const unsigned int* scale_bits;  // float bits of max |position coordinate| over E1 and E2 (written by the gather kernel)
 };
 
 template <int D>
@@ -247,7 +253,13 @@ template <> struct Quad<double> {
 // MIRROR (unsharded handles): the score is symmetric in (i,j) bit for bit, so only tiles that touch the
 // upper triangle are computed; every value s(i,j), i<j, is stored at [i][j] (row-wise float4) and mirrored
 // to [j][i] (the lane's 4 rows of one column are 16 contiguous bytes of row j).  Halves the fp64 work.
-template <typename T, int KIND, int D, bool MIRROR>
+// FILTER (compile-time dimension only): the kernel is bound by fp64 arithmetic (two square roots and an exp
+// per pair), yet only ~15 % of the pairs pass the consistency test |l1 - l2| < epsilon.  Every pair is first
+// screened in fp32 against epsilon + a rigorous error margin (a pair is dropped only when the exact test must
+// fail too, so every stored value is still produced by the exact fp64 path below, bit for bit); the survivors
+// of a warp's 4 x 128 block are compacted into a shared-memory queue and scored 32 at a time with all lanes
+// busy, the results pass through a shared-memory copy of the block so that the stores stay row-wise float4.
+template <typename T, int KIND, int D, bool MIRROR, bool FILTER>
 __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
   constexpr int DD = (KIND == 1) ? 6 : D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,6 +275,75 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) out[q][e] = encode<T>(0.0, false);
 
+  if constexpr (FILTER && DD > 0) {
+    __shared__ unsigned short queue[kWarps][kRowsPerWarp * 128];
+    __shared__ __align__(16) T tile[kWarps][kRowsPerWarp][128];
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) Quad<T>::store(&tile[warp][q][lane * 4], out[q]);
+    // Screening threshold.  With R = max |coordinate|, u = 2^-24: converting the inputs, the subtraction, the
+    // three-term sum of squares and the approximate square root put the fp32 length within 40 u R of the exact
+    // one (d <= 3); 1024 u R covers both lengths and the final subtraction with a wide margin.  NaN / Inf
+    // anywhere makes the comparison below false, i.e. the pair goes to the exact path.
+    const float R = __uint_as_float(*a.scale_bits);
+    const double eps = (KIND == 1) ? a.p1 : a.p1;
+    const float thr = __double2float_ru((eps + 1024.0 * 5.9604644775390625e-08 * (double)R) * (1.0 + 9.5367431640625e-07));
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = c0 + e;
+      const bool jok = (j < a.m) && !(MIRROR && j <= a.row0 + lr0);
+      int aj0 = -1, aj1 = -1;
+      float4 f1j = make_float4(0.f, 0.f, 0.f, 0.f), f2j = f1j;
+      if (jok) { aj0 = __ldg(a.A0 + j); aj1 = __ldg(a.A1 + j); f1j = __ldg(a.F1 + j); f2j = __ldg(a.F2 + j); }
+#pragma unroll
+      for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int li = lr0 + q;
+        const int i = a.row0 + li;
+        bool cand = jok && li < a.rows && i != j && !(MIRROR && j < i);
+        if (cand) {
+          const int ai0 = __ldg(a.A0 + i), ai1 = __ldg(a.A1 + i);
+          cand = (ai0 != aj0) && (ai1 != aj1);  // distinctness (ref clipper.cpp:35-38)
+          const float4 f1i = __ldg(a.F1 + i), f2i = __ldg(a.F2 + i);
+          const float x1 = f1i.x - f1j.x, y1 = f1i.y - f1j.y, z1 = f1i.z - f1j.z;
+          const float x2 = f2i.x - f2j.x, y2 = f2i.y - f2j.y, z2 = f2i.z - f2j.z;
+          const float l1 = sqrtf(fmaf(z1, z1, fmaf(y1, y1, x1 * x1)));
+          const float l2 = sqrtf(fmaf(z2, z2, fmaf(y2, y2, x2 * x2)));
+          if (fabsf(l1 - l2) >= thr) cand = false;  // certainly inconsistent
+        }
+        const unsigned int vote = __ballot_sync(0xffffffffu, cand);
+        if (cand) queue[warp][cnt + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)((q << 7) | (e << 5) | lane);
+        cnt += __popc(vote);
+      }
+    }
+    __syncwarp();
+    for (unsigned int k = lane; k < cnt; k += 32) {
+      const unsigned int code = queue[warp][k];
+      const int q = code >> 7, e = (code >> 5) & 3, l = code & 31;
+      const int i = a.row0 + lr0 + q, j = blockIdx.x * 128 + l * 4 + e;
+      double e1i[DD], e2i[DD], e1j[DD], e2j[DD];
+#pragma unroll
+      for (int t = 0; t < DD; ++t) {
+        e1i[t] = __ldg(a.E1 + (size_t)i * DD + t); e2i[t] = __ldg(a.E2 + (size_t)i * DD + t);
+        e1j[t] = __ldg(a.E1 + (size_t)j * DD + t); e2j[t] = __ldg(a.E2 + (size_t)j * DD + t);
+      }
+      double scr;
+      if (KIND == 0) {
+        const double l1 = point_dist<DD>(e1i, e1j, 0), l2 = point_dist<DD>(e2i, e2j, 0);
+        scr = euclid_score(l1, l2, a.p0, a.p1, a.p2);
+      } else {
+        const double l1 = point_dist<3>(e1i, e1j, 0), l2 = point_dist<3>(e2i, e2j, 0);
+        const double dot1 = __dadd_rn(__dadd_rn(__dmul_rn(e1i[3], e1j[3]), __dmul_rn(e1i[4], e1j[4])), __dmul_rn(e1i[5], e1j[5]));
+        const double dot2 = __dadd_rn(__dadd_rn(__dmul_rn(e2i[3], e2j[3]), __dmul_rn(e2i[4], e2j[4])), __dmul_rn(e2i[5], e2j[5]));
+        scr = pointnormal_score(l1, l2, dot1, dot2, a.p0, a.p1, a.p2, a.p3);
+      }
+      if (scr > a.affinityeps) tile[warp][q][l * 4 + e] = encode<T>(scr, true);  // ref clipper.cpp:53-55
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) out[q][e] = tile[warp][q][lane * 4 + e];
+  } else {
   // row endpoints are warp-uniform: fetched through the read-only path as broadcasts
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -305,6 +386,7 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
       if (scr > a.affinityeps) out[q][e] = encode<T>(scr, true);  // ref clipper.cpp:53-55
     }
   }
+  }  // !FILTER
   if (!MIRROR) {
 #pragma unroll
     for (int q = 0; q < kRowsPerWarp; ++q) {
@@ -344,15 +426,33 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
 // E1[i][:] = D1[:, A(i,0)], E2[i][:] = D2[:, A(i,1)]; flags out-of-range association indices
 __global__ void gather_endpoints_kernel(const double* D1, const double* D2, const int* A0, const int* A1,
                                         int m, int d, long long n1, long long n2, double* E1, double* E2,
-                                        int* error) {
+                                        float4* F1, float4* F2, unsigned int* scale_bits, int* error) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const int a0 = A0[i], a1 = A1[i];
-  if (a0 < 0 || a0 >= n1 || a1 < 0 || a1 >= n2) { atomicExch(error, 2); return; }
-  for (int q = 0; q < d; ++q) {
-    E1[(size_t)i * d + q] = D1[(size_t)a0 * d + q];
-    E2[(size_t)i * d + q] = D2[(size_t)a1 * d + q];
+  float big = 0.f;
+  if (i < m) {
+    const int a0 = A0[i], a1 = A1[i];
+    if (a0 < 0 || a0 >= n1 || a1 < 0 || a1 >= n2) { atomicExch(error, 2); }
+    else {
+      float f1[3] = {0.f, 0.f, 0.f}, f2[3] = {0.f, 0.f, 0.f};
+      for (int q = 0; q < d; ++q) {
+        const double x1 = D1[(size_t)a0 * d + q], x2 = D2[(size_t)a1 * d + q];
+        E1[(size_t)i * d + q] = x1;
+        E2[(size_t)i * d + q] = x2;
+        if (q < 3) {  // positions (point-normal data: normals follow)
+          f1[q] = (float)x1; f2[q] = (float)x2;
+          // NaN must not be lost in the maximum: it becomes +Inf (margin = Inf: every pair takes the exact path)
+          const float m1 = fabsf(f1[q]), m2 = fabsf(f2[q]);
+          big = fmaxf(big, (m1 == m1) ? m1 : __int_as_float(0x7f800000));
+          big = fmaxf(big, (m2 == m2) ? m2 : __int_as_float(0x7f800000));
+        }
+      }
+      F1[i] = make_float4(f1[0], f1[1], f1[2], 0.f);
+      F2[i] = make_float4(f2[0], f2[1], f2[2], 0.f);
+    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) big = fmaxf(big, __shfl_xor_sync(0xffffffffu, big, o));
+  if ((threadIdx.x & 31) == 0 && big > 0.f) atomicMax(scale_bits, __float_as_uint(big));  // non-negative floats order like their bits
 }
 
 // ------------------------------------------------------------------------------------------
@@ -418,15 +518,57 @@ __device__ void stage_segment(const StageArgs& s, const Plan& p, int m, int seg,
   const double nrm = sqrt(s.z);
   const int cbeg = seg * p.W;
   double part = 0.0;
-  for (int c = threadIdx.x; c < p.W; c += kThreads) {
-    const int j = cbeg + c;
-    double v = 0.0;
-    if (j < m) {
-      v = staged_value(s, j, nrm);
-      if (owner && s.dst) s.dst[j] = v;
+  // four columns per thread and trip: the LL cells (and u) of all four are requested before the first tag is
+  // looked at -- one L2 round trip per trip instead of one per column (the spin loop of ll_load would otherwise
+  // serialise them); a cell whose tag is not there yet falls back to ll_load.
+  constexpr int kBatch = 4;
+  for (int c = threadIdx.x; c < p.W; c += kBatch * kThreads) {
+    double v[kBatch];
+    if (s.mode == STAGE_RAW) {
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int cc = c + b * kThreads, j = cbeg + cc;
+        v[b] = (cc < p.W && j < m) ? s.srcA[j] : 0.0;
+      }
+    } else {
+      const uint4* cells = (s.mode == STAGE_DIV) ? s.llA : s.llB;
+      unsigned lo[kBatch], t1[kBatch], hi[kBatch], t2[kBatch];
+      double ua[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int cc = c + b * kThreads, j = cbeg + cc;
+        lo[b] = hi[b] = 0u; t1[b] = t2[b] = s.tag; ua[b] = 0.0;
+        if (cc < p.W && j < m) {
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(lo[b]), "=r"(t1[b]), "=r"(hi[b]), "=r"(t2[b]) : "l"(cells + j) : "memory");
+          if (s.mode == STAGE_STEP) ua[b] = s.srcA[j];
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int cc = c + b * kThreads, j = cbeg + cc;
+        v[b] = 0.0;
+        if (cc < p.W && j < m) {
+          const double x = (t1[b] == s.tag && t2[b] == s.tag) ? __hiloint2double((int)hi[b], (int)lo[b])
+                                                              : ll_load(cells + j, s.tag, s.error);
+          if (s.mode == STAGE_DIV) v[b] = x / nrm;
+          else {
+            double w = __dadd_rn(ua[b], __dmul_rn(s.alpha, x));
+            w = (w < 0.0) ? 0.0 : w;
+            v[b] = (s.z > 0.0) ? w / nrm : w;
+          }
+        }
+      }
     }
-    vs[vs_pos<T>(c)] = v;
-    part += v;
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int cc = c + b * kThreads, j = cbeg + cc;
+      if (cc < p.W) {
+        if (owner && s.dst && j < m) s.dst[j] = v[b];
+        vs[vs_pos<T>(cc)] = v[b];
+        part += v[b];
+      }
+    }
   }
   if (owner) {  // deterministic block sum: warp butterflies, then warp 0 adds the 8 partials in order
     part = warp_sum(part);
