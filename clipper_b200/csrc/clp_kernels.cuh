@@ -195,6 +195,12 @@ struct ScoreArgs {
   const unsigned int* scale_bits;  // float bits of max |position coordinate| over E1 and E2 (written by the gather kernel)
 };
 
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT, relative error <= 2^-22
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <int D>
 __device__ __forceinline__ double point_dist(const double* a, const double* b, int d_rt) {
   double s = 0.0;
@@ -269,47 +275,60 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
   T* Mbase = reinterpret_cast<T*>(a.M);
   const int dd = (DD > 0) ? DD : a.d;
 
+  // FILTER: survivor queue of every warp and the CTA's 32 x 128 block (row stride 132: the transposed reads of
+  // the mirror stores hit 8 banks instead of 1)
+  constexpr bool kF = FILTER && DD > 0;
+  __shared__ unsigned short queue[kF ? kWarps : 1][kF ? kRowsPerWarp * 128 : 1];
+  __shared__ __align__(16) T tile[kF ? kRowTile : 1][kF ? 132 : 4];
+
   T out[kRowsPerWarp][4];
 #pragma unroll
   for (int q = 0; q < kRowsPerWarp; ++q)
 #pragma unroll
     for (int e = 0; e < 4; ++e) out[q][e] = encode<T>(0.0, false);
 
-  if constexpr (FILTER && DD > 0) {
-    __shared__ unsigned short queue[kWarps][kRowsPerWarp * 128];
-    __shared__ __align__(16) T tile[kWarps][kRowsPerWarp][128];
+  if constexpr (kF) {
 #pragma unroll
-    for (int q = 0; q < kRowsPerWarp; ++q) Quad<T>::store(&tile[warp][q][lane * 4], out[q]);
-    // Screening threshold.  With R = max |coordinate|, u = 2^-24: converting the inputs, the subtraction, the
-    // three-term sum of squares and the approximate square root put the fp32 length within 40 u R of the exact
-    // one (d <= 3); 1024 u R covers both lengths and the final subtraction with a wide margin.  NaN / Inf
-    // anywhere makes the comparison below false, i.e. the pair goes to the exact path.
+    for (int q = 0; q < kRowsPerWarp; ++q) Quad<T>::store(&tile[warp * kRowsPerWarp + q][lane * 4], out[q]);
+    // Screening threshold.  With R = max |coordinate|, u = 2^-24: converting the inputs (u R per coordinate), the
+    // subtraction (2 u R more), the three-term sum of squares (3 u relative) and sqrt.approx (2^-22 relative) put
+    // the fp32 length within 7 u R + 10 u l <= 42 u R of the exact one (d <= 3, l <= 2 sqrt(3) R); the final
+    // subtraction adds at most 4 u R: |c32 - c| < 90 u R, and 1024 u R is used.  NaN / Inf anywhere makes the
+    // comparison below false, i.e. the pair goes to the exact path.
     const float R = __uint_as_float(*a.scale_bits);
     const double eps = (KIND == 1) ? a.p1 : a.p1;
     const float thr = __double2float_ru((eps + 1024.0 * 5.9604644775390625e-08 * (double)R) * (1.0 + 9.5367431640625e-07));
     unsigned int cnt = 0;
+    // the warp's four rows: association pair and fp32 positions, fetched once (warp-uniform broadcasts)
+    int ai0[kRowsPerWarp], ai1[kRowsPerWarp];
+    float4 f1i[kRowsPerWarp], f2i[kRowsPerWarp];
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+      const int li = lr0 + q;
+      ai0[q] = ai1[q] = -1; f1i[q] = f2i[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (li < a.rows) {
+        const int i = a.row0 + li;
+        ai0[q] = __ldg(a.A0 + i); ai1[q] = __ldg(a.A1 + i); f1i[q] = __ldg(a.F1 + i); f2i[q] = __ldg(a.F2 + i);
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = c0 + e;
       const bool jok = (j < a.m) && !(MIRROR && j <= a.row0 + lr0);
-      int aj0 = -1, aj1 = -1;
+      int aj0 = -2, aj1 = -2;
       float4 f1j = make_float4(0.f, 0.f, 0.f, 0.f), f2j = f1j;
       if (jok) { aj0 = __ldg(a.A0 + j); aj1 = __ldg(a.A1 + j); f1j = __ldg(a.F1 + j); f2j = __ldg(a.F2 + j); }
 #pragma unroll
       for (int q = 0; q < kRowsPerWarp; ++q) {
         const int li = lr0 + q;
         const int i = a.row0 + li;
-        bool cand = jok && li < a.rows && i != j && !(MIRROR && j < i);
-        if (cand) {
-          const int ai0 = __ldg(a.A0 + i), ai1 = __ldg(a.A1 + i);
-          cand = (ai0 != aj0) && (ai1 != aj1);  // distinctness (ref clipper.cpp:35-38)
-          const float4 f1i = __ldg(a.F1 + i), f2i = __ldg(a.F2 + i);
-          const float x1 = f1i.x - f1j.x, y1 = f1i.y - f1j.y, z1 = f1i.z - f1j.z;
-          const float x2 = f2i.x - f2j.x, y2 = f2i.y - f2j.y, z2 = f2i.z - f2j.z;
-          const float l1 = sqrtf(fmaf(z1, z1, fmaf(y1, y1, x1 * x1)));
-          const float l2 = sqrtf(fmaf(z2, z2, fmaf(y2, y2, x2 * x2)));
-          if (fabsf(l1 - l2) >= thr) cand = false;  // certainly inconsistent
-        }
+        const float x1 = f1i[q].x - f1j.x, y1 = f1i[q].y - f1j.y, z1 = f1i[q].z - f1j.z;
+        const float x2 = f2i[q].x - f2j.x, y2 = f2i[q].y - f2j.y, z2 = f2i[q].z - f2j.z;
+        const float l1 = sqrt_approx(fmaf(z1, z1, fmaf(y1, y1, x1 * x1)));
+        const float l2 = sqrt_approx(fmaf(z2, z2, fmaf(y2, y2, x2 * x2)));
+        // distinctness (ref clipper.cpp:35-38); "certainly inconsistent" last: a NaN keeps the pair
+        const bool cand = jok && li < a.rows && i != j && !(MIRROR && j < i) && ai0[q] != aj0 && ai1[q] != aj1 &&
+                          !(fabsf(l1 - l2) >= thr);
         const unsigned int vote = __ballot_sync(0xffffffffu, cand);
         if (cand) queue[warp][cnt + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)((q << 7) | (e << 5) | lane);
         cnt += __popc(vote);
@@ -336,13 +355,13 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
         const double dot2 = __dadd_rn(__dadd_rn(__dmul_rn(e2i[3], e2j[3]), __dmul_rn(e2i[4], e2j[4])), __dmul_rn(e2i[5], e2j[5]));
         scr = pointnormal_score(l1, l2, dot1, dot2, a.p0, a.p1, a.p2, a.p3);
       }
-      if (scr > a.affinityeps) tile[warp][q][l * 4 + e] = encode<T>(scr, true);  // ref clipper.cpp:53-55
+      if (scr > a.affinityeps) tile[warp * kRowsPerWarp + q][l * 4 + e] = encode<T>(scr, true);  // ref clipper.cpp:53-55
     }
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < kRowsPerWarp; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) out[q][e] = tile[warp][q][lane * 4 + e];
+      for (int e = 0; e < 4; ++e) out[q][e] = tile[warp * kRowsPerWarp + q][lane * 4 + e];
   } else {
   // row endpoints are warp-uniform: fetched through the read-only path as broadcasts
 #pragma unroll
@@ -407,6 +426,17 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
       for (int e = 0; e < 4; ++e)
         if (c0 + e >= i) Mbase[(size_t)i * a.ld + c0 + e] = out[q][e];
     }
+  }
+  if constexpr (kF) {
+    // ... and the mirror image through the shared-memory block: column cc of the block is 32 consecutive
+    // elements (one 128-byte line) of row j = column index, stored by one warp instruction
+    __syncthreads();
+    const int i = blockIdx.y * kRowTile + lane;
+    for (int cc = warp; cc < 128; cc += kWarps) {
+      const int j = blockIdx.x * 128 + cc;
+      if (j < a.rows_pad && i < j && i < a.ld) Mbase[(size_t)j * a.ld + i] = tile[lane][cc];
+    }
+    return;
   }
   // ... and the mirror image: column j of this thread's 4 rows is 4 consecutive elements of row j
 #pragma unroll
