@@ -87,6 +87,9 @@ struct clp_handle_s {
   DevBuf A_dev;                 // int32 [2m]
   DevBuf E1, E2, D1dev, D2dev, F12;  // F12: fp32 positions of both endpoints (screening pass of the scoring kernel)
   int score_filter = env_int("CLP_SCORE_FILTER", 1);
+  int fuse_count = env_int("CLP_FUSE_COUNT", 1);  // scoring kernel counts the kept entries (skips sparse_count_kernel)
+  bool counts_fused = false;                        // sp_ptr4 already holds the counts of the current matrix
+  int fill_items = env_int("CLP_FILL_ITEMS", 1);  // compact copy written item-wise (coalesced) instead of row-wise
 
   // solver workspace
   DevBuf vecs;    // V_SLOTS x mpad doubles: U0 U1 MV0 MV1 CV0 CV1 (local only)
@@ -253,15 +256,19 @@ int build_sparse(clp_handle h, bool force) {
   const Plan& p = h->plan;
   const int nseg = p.NSEG;
   const long long nptr = (long long)nseg * (h->rows_pad + 1);
-  CLP_CUDA(h, h->sp_ptr4.ensure((size_t)nptr * sizeof(unsigned int)));
-  CLP_CUDA(h, cudaMemsetAsync(h->sp_ptr4.p, 0, (size_t)nptr * sizeof(unsigned int), h->stream));
+  const bool fused = h->counts_fused;  // counts produced by the scoring kernel (scored matrices are "plain")
+  h->counts_fused = false;
   if (int rc = reset_sync(h)) return rc;
   SyncBlock* sb = h->sync.as<SyncBlock>();
   const T* M = h->Mbuf.as<T>();
   const unsigned blocks = (unsigned)(((size_t)h->rows_pad * 32 + 255) / 256);
-  sparse_count_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
-                                                        h->sp_ptr4.as<unsigned int>(), &sb->counts[0]);
-  CLP_CUDA(h, cudaGetLastError());
+  if (!fused) {
+    CLP_CUDA(h, h->sp_ptr4.ensure((size_t)nptr * sizeof(unsigned int)));
+    CLP_CUDA(h, cudaMemsetAsync(h->sp_ptr4.p, 0, (size_t)nptr * sizeof(unsigned int), h->stream));
+    sparse_count_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
+                                                          h->sp_ptr4.as<unsigned int>(), &sb->counts[0]);
+    CLP_CUDA(h, cudaGetLastError());
+  }
   // sort the rows of every segment by slice length, group them four at a time, scan the item lengths
   const int NI = h->rows_pad / 4;
   const long long nitem = (long long)nseg * (NI + 1);
@@ -269,7 +276,7 @@ int build_sparse(clp_handle h, bool force) {
   CLP_CUDA(h, h->sp_rank.ensure((size_t)nseg * h->rows_pad * sizeof(unsigned int)));
   CLP_CUDA(h, h->sp_item.ensure((size_t)nitem * sizeof(unsigned int)));
   sell_sort_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad, h->sp_rowid.as<unsigned int>(),
-                                                 h->sp_rank.as<unsigned int>());
+                                                 h->sp_rank.as<unsigned int>(), fused ? &sb->counts[0] : nullptr);
   CLP_CUDA(h, cudaGetLastError());
   sell_itemlen_kernel<<<(unsigned)((nitem + 255) / 256), 256, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->sp_rowid.as<unsigned int>(),
                                                                               h->rows_pad, nseg, h->sp_item.as<unsigned int>());
@@ -295,10 +302,17 @@ int build_sparse(clp_handle h, bool force) {
   if (!force && !(sparse_bytes < 0.8 * dense_bytes)) return 1;  // keep a dense sweep
   CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(T)));
   CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(unsigned short)));
-  sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
-                                                       h->sp_item.as<unsigned int>(), h->sp_rank.as<unsigned int>(),
-                                                       h->sp_val.as<T>(), h->sp_col.as<unsigned short>(),
-                                                       std::getenv("CLP_PROBE_NO_CONFLICT") ? 1 : 0);
+  if (h->fill_items && !std::getenv("CLP_PROBE_NO_CONFLICT")) {
+    const long long nwarp = (long long)nseg * NI;
+    sparse_fill_items_kernel<T><<<(unsigned)((nwarp + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0, h->stream>>>(
+        M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg, h->sp_item.as<unsigned int>(), h->sp_rowid.as<unsigned int>(),
+        h->sp_val.as<T>(), h->sp_col.as<unsigned short>());
+  } else {
+    sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
+                                                         h->sp_item.as<unsigned int>(), h->sp_rank.as<unsigned int>(),
+                                                         h->sp_val.as<T>(), h->sp_col.as<unsigned short>(),
+                                                         std::getenv("CLP_PROBE_NO_CONFLICT") ? 1 : 0);
+  }
   CLP_CUDA(h, cudaGetLastError());
   h->sp.val = h->sp_val.p; h->sp.off16 = h->sp_col.as<unsigned short>();
   h->sp.itemptr = h->sp_item.as<unsigned int>(); h->sp.rowid = h->sp_rowid.as<unsigned int>(); h->sp.rows_pad = h->rows_pad;
@@ -401,12 +415,17 @@ int read_sync(clp_handle h, SyncBlock* sb) {
 template <typename T, bool MIRROR>
 int launch_score_m(clp_handle h, int kind, int d, const ScoreArgs& a) {
   dim3 grid((unsigned)(h->ld / 128), (unsigned)(h->rows_pad / kRowTile));
-  if (h->score_filter) {
+  if constexpr (sizeof(T) == 4) {  // the screened kernel's shared-memory block is sized for fp32 storage
+   if (h->score_filter) {
     if (kind == 1) score_tile_kernel<T, 1, 6, MIRROR, true><<<grid, kThreads, 0, h->stream>>>(a);
     else if (d == 3) score_tile_kernel<T, 0, 3, MIRROR, true><<<grid, kThreads, 0, h->stream>>>(a);
     else if (d == 2) score_tile_kernel<T, 0, 2, MIRROR, true><<<grid, kThreads, 0, h->stream>>>(a);
     else score_tile_kernel<T, 0, 0, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
-  } else {
+    CLP_CUDA(h, cudaGetLastError());
+    return CLP_OK;
+   }
+  }
+  {
     if (kind == 1) score_tile_kernel<T, 1, 6, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
     else if (d == 3) score_tile_kernel<T, 0, 3, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
     else if (d == 2) score_tile_kernel<T, 0, 2, MIRROR, false><<<grid, kThreads, 0, h->stream>>>(a);
@@ -440,6 +459,17 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   a.A0 = Ad; a.A1 = Ad + m;
   a.M = h->Mbuf.p; a.ld = h->ld; a.m = (int)m; a.row0 = h->row0; a.rows = h->rows; a.rows_pad = h->rows_pad;
   a.F1 = h->F12.as<float4>(); a.F2 = a.F1 + m; a.scale_bits = &sb->scale_bits;
+  a.cnt = nullptr; a.W = h->plan.W;
+  h->counts_fused = false;
+  if (h->score_filter && h->fuse_count && h->storage == CLP_STORE_F32 && (kind == 1 || d == 2 || d == 3) &&
+      (h->dense_mode == 3 || h->dense_mode == 4)) {
+    // the screened scoring kernel also counts the kept entries per (segment, row): first pass of the compact build
+    const size_t nptr = (size_t)h->plan.NSEG * (h->rows_pad + 1);
+    CLP_CUDA(h, h->sp_ptr4.ensure(nptr * sizeof(unsigned int)));
+    CLP_CUDA(h, cudaMemsetAsync(h->sp_ptr4.p, 0, nptr * sizeof(unsigned int), h->stream));
+    a.cnt = h->sp_ptr4.as<unsigned int>();
+    h->counts_fused = true;
+  }
   a.d = d; a.p0 = p0; a.p1 = p1; a.p2 = p2; a.p3 = p3; a.affinityeps = h->prm.affinityeps;
   int rc = (h->storage == CLP_STORE_F64) ? launch_score<double>(h, kind, d, a) : launch_score<float>(h, kind, d, a);
   if (rc) return rc;

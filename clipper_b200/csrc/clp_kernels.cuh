@@ -72,6 +72,11 @@ template <> __device__ __forceinline__ double encode<double>(double mval, bool c
   const double a = fabs(mval);
   return cbit ? a : -a;
 }
+template <typename T> __device__ __forceinline__ bool is_neutral(T s);
+template <> __device__ __forceinline__ bool is_neutral<float>(float s) { return __float_as_uint(s) == 0x80000000u; }
+template <> __device__ __forceinline__ bool is_neutral<double>(double s) {
+  return (unsigned long long)__double_as_longlong(s) == 0x8000000000000000ULL;
+}
 
 // ------------------------------------------------------------------------------------------
 // device-wide barrier for the persistent kernel (all CTAs co-resident: cooperative launch).
@@ -193,6 +198,10 @@ struct ScoreArgs {
   const float4* F1;  // [m] (x, y, z, 0) of E1
   const float4* F2;  // [m]
   const unsigned int* scale_bits;  // float bits of max |position coordinate| over E1 and E2 (written by the gather kernel)
+  // optional by-product (FILTER instances): kept entries per (column segment, local row), the first pass of the
+  // compact-copy build (clp_sparse.cuh); zeroed by the host, += by the kernel
+  unsigned int* cnt;  // [NSEG][rows_pad + 1] or null
+  int W;              // segment width (multiple of 128)
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT, relative error <= 2^-22
@@ -280,6 +289,11 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
   constexpr bool kF = FILTER && DD > 0;
   __shared__ unsigned short queue[kF ? kWarps : 1][kF ? kRowsPerWarp * 128 : 1];
   __shared__ __align__(16) T tile[kF ? kRowTile : 1][kF ? 132 : 4];
+  // fp64 endpoints of the block's 128 columns and 32 rows (E1 then E2; odd row stride against bank conflicts):
+  // the survivors' scattered 8-byte reads would otherwise keep the L1 data path 86 % busy
+  constexpr int kES = 2 * (DD > 0 ? DD : 1) + 1;
+  __shared__ double colE[kF ? 128 : 1][kES];
+  __shared__ double rowE[kF ? kRowTile : 1][kES];
 
   T out[kRowsPerWarp][4];
 #pragma unroll
@@ -288,6 +302,17 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
     for (int e = 0; e < 4; ++e) out[q][e] = encode<T>(0.0, false);
 
   if constexpr (kF) {
+    for (int idx = threadIdx.x; idx < 128 * DD; idx += kThreads) {
+      const int c = idx / DD, t = idx - c * DD, j = blockIdx.x * 128 + c;
+      colE[c][t] = (j < a.m) ? __ldg(a.E1 + (size_t)j * DD + t) : 0.0;
+      colE[c][DD + t] = (j < a.m) ? __ldg(a.E2 + (size_t)j * DD + t) : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < kRowTile * DD; idx += kThreads) {
+      const int r = idx / DD, t = idx - r * DD, li = blockIdx.y * kRowTile + r;
+      rowE[r][t] = (li < a.rows) ? __ldg(a.E1 + (size_t)(a.row0 + li) * DD + t) : 0.0;
+      rowE[r][DD + t] = (li < a.rows) ? __ldg(a.E2 + (size_t)(a.row0 + li) * DD + t) : 0.0;
+    }
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < kRowsPerWarp; ++q) Quad<T>::store(&tile[warp * kRowsPerWarp + q][lane * 4], out[q]);
     // Screening threshold.  With R = max |coordinate|, u = 2^-24: converting the inputs (u R per coordinate), the
@@ -338,12 +363,12 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
     for (unsigned int k = lane; k < cnt; k += 32) {
       const unsigned int code = queue[warp][k];
       const int q = code >> 7, e = (code >> 5) & 3, l = code & 31;
-      const int i = a.row0 + lr0 + q, j = blockIdx.x * 128 + l * 4 + e;
+      const int r = warp * kRowsPerWarp + q, c = l * 4 + e;
       double e1i[DD], e2i[DD], e1j[DD], e2j[DD];
 #pragma unroll
       for (int t = 0; t < DD; ++t) {
-        e1i[t] = __ldg(a.E1 + (size_t)i * DD + t); e2i[t] = __ldg(a.E2 + (size_t)i * DD + t);
-        e1j[t] = __ldg(a.E1 + (size_t)j * DD + t); e2j[t] = __ldg(a.E2 + (size_t)j * DD + t);
+        e1i[t] = rowE[r][t]; e2i[t] = rowE[r][DD + t];
+        e1j[t] = colE[c][t]; e2j[t] = colE[c][DD + t];
       }
       double scr;
       if (KIND == 0) {
@@ -362,6 +387,19 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
     for (int q = 0; q < kRowsPerWarp; ++q)
 #pragma unroll
       for (int e = 0; e < 4; ++e) out[q][e] = tile[warp * kRowsPerWarp + q][lane * 4 + e];
+    if (a.cnt) {  // kept entries of the warp's four rows in this 128-column block (one column segment)
+      unsigned int packed = 0;  // four 8-bit fields, <= 128 each after the warp sum
+#pragma unroll
+      for (int q = 0; q < kRowsPerWarp; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) packed += (is_neutral<T>(out[q][e]) ? 0u : 1u) << (8 * q);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
+      if (lane < kRowsPerWarp) {
+        const unsigned int c = (packed >> (8 * lane)) & 0xffu;
+        if (c) atomicAdd(a.cnt + (size_t)((blockIdx.x * 128) / a.W) * (a.rows_pad + 1) + lr0 + lane, c);
+      }
+    }
   } else {
   // row endpoints are warp-uniform: fetched through the read-only path as broadcasts
 #pragma unroll
@@ -434,7 +472,13 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
     const int i = blockIdx.y * kRowTile + lane;
     for (int cc = warp; cc < 128; cc += kWarps) {
       const int j = blockIdx.x * 128 + cc;
-      if (j < a.rows_pad && i < j && i < a.ld) Mbase[(size_t)j * a.ld + i] = tile[lane][cc];
+      const bool st = j < a.rows_pad && i < j && i < a.ld;
+      const T v = tile[lane][cc];
+      if (st) Mbase[(size_t)j * a.ld + i] = v;
+      if (a.cnt) {  // the same 32 entries are a piece of row j inside the segment of this block's rows
+        const unsigned int vote = __ballot_sync(0xffffffffu, st && !is_neutral<T>(v));
+        if (lane == 0 && vote) atomicAdd(a.cnt + (size_t)((blockIdx.y * kRowTile) / a.W) * (a.rows_pad + 1) + j, (unsigned int)__popc(vote));
+      }
     }
     return;
   }

@@ -48,15 +48,20 @@ struct SparseView {
   int head_where;                // 1: before the wait that ends the combine step, 2: also before the one that ends the sweep
 };
 
-template <typename T> __device__ __forceinline__ bool is_neutral(T s);
-template <> __device__ __forceinline__ bool is_neutral<float>(float s) { return __float_as_uint(s) == 0x80000000u; }
-template <> __device__ __forceinline__ bool is_neutral<double>(double s) {
-  return (unsigned long long)__double_as_longlong(s) == 0x8000000000000000ULL;
+template <typename T> __device__ __forceinline__ void load4(const T* p, T (&x)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&x)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
 }
+template <> __device__ __forceinline__ void load4<double>(const double* p, double (&x)[4]) {
+  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+
 template <typename T> __device__ __forceinline__ bool is_plain(T s) { return s > T(0); }
 
 // pass 1: one warp per (padded) local row counts the kept entries per column segment:
-//   cnt4[seg * (rows_pad + 1) + row] = number of 4-entry units of slice (row, seg)
+//   cnt4[seg * (rows_pad + 1) + row] = kept entries of slice (row, seg)   (the scoring kernel can produce the
+//   same array on the fly: ScoreArgs::cnt)
 //   totals[0] += kept entries, totals[1] += kept entries that are not "plain"
 template <typename T>
 __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
@@ -69,15 +74,16 @@ __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, i
     if (warp < rows) {
       const int c0 = s * W, c1 = min(m, c0 + W);
       for (int j = c0 + lane * 4; j < c1; j += 128) {
-        const T* p = M + (size_t)warp * ld + j;
+        T x[4];
+        load4<T>(M + (size_t)warp * ld + j, x);  // j + 3 < ld: ld is a multiple of 128
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (j + e < c1 && !is_neutral<T>(p[e])) { ++c; o += is_plain<T>(p[e]) ? 0u : 1u; }
+          if (j + e < c1 && !is_neutral<T>(x[e])) { ++c; o += is_plain<T>(x[e]) ? 0u : 1u; }
       }
     }
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, k); o += __shfl_xor_sync(0xffffffffu, o, k); }
-    if (lane == 0) cnt4[(size_t)s * (rows_pad + 1) + warp] = (c + 3u) >> 2;
+    if (lane == 0) cnt4[(size_t)s * (rows_pad + 1) + warp] = c;
     real += c; odd += o;
   }
   if (lane == 0) {
@@ -89,13 +95,20 @@ __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, i
 // pass 2: one block per column segment sorts the rows by slice length, longest first (counting sort over the
 // <= 1025 possible lengths; ties in arrival order, which does not influence any result).
 //   rowid[seg][pos] = row at sorted position pos, rank[seg][row] = its position
-__global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, unsigned int* rowid, unsigned int* rank) {
+__global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, unsigned int* rowid, unsigned int* rank,
+                                 unsigned long long* total_entries /* nullable: += kept entries */) {
   __shared__ unsigned int hist[kSegMax / 4 + 2];
   const int nb = kSegMax / 4 + 1;
   const unsigned int* c = cnt4 + (size_t)blockIdx.x * (rows_pad + 1);
   for (int i = threadIdx.x; i <= nb; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
-  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) atomicAdd(&hist[min(c[r], (unsigned int)(nb - 1))], 1u);
+  unsigned long long mine = 0;
+  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) { mine += c[r]; atomicAdd(&hist[min((c[r] + 3u) >> 2, (unsigned int)(nb - 1))], 1u); }
+  if (total_entries) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total_entries, mine);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {  // start of every length class, longest class first
     unsigned int run = 0;
@@ -103,7 +116,7 @@ __global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, unsigne
   }
   __syncthreads();
   for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) {
-    const unsigned int pos = atomicAdd(&hist[min(c[r], (unsigned int)(nb - 1))], 1u);
+    const unsigned int pos = atomicAdd(&hist[min((c[r] + 3u) >> 2, (unsigned int)(nb - 1))], 1u);
     rowid[(size_t)blockIdx.x * rows_pad + pos] = (unsigned int)r;
     rank[(size_t)blockIdx.x * rows_pad + r] = pos;
   }
@@ -118,7 +131,7 @@ __global__ void sell_itemlen_kernel(const unsigned int* cnt4, const unsigned int
   if (t >= (long long)nseg * (NI + 1)) return;
   const int seg = (int)(t / (NI + 1)), i = (int)(t - (long long)seg * (NI + 1));
   unsigned int len = 0u;
-  if (i < NI) len = 4u * cnt4[(size_t)seg * (rows_pad + 1) + rowid[(size_t)seg * rows_pad + 4 * i]];
+  if (i < NI) len = 4u * ((cnt4[(size_t)seg * (rows_pad + 1) + rowid[(size_t)seg * rows_pad + 4 * i]] + 3u) >> 2);
   itemptr[t] = len;
 }
 
@@ -219,6 +232,97 @@ __global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, in
       const unsigned long long at = base + 16ull * (w >> 2) + (w & 3u);
       val[at] = encode<T>(0.0, false); off16[at] = (unsigned short)kZeroSlot;
     }
+  }
+}
+
+// pass 4, item-wise: one warp per item reads its four member rows together and compacts them through four
+// shared-memory rings; chunk k of all four members is then 64 contiguous bytes of val (32 of off16), so a flush
+// of 8 chunks per member is one fully coalesced 512-byte store (the row-wise kernel above issues 4- and 2-byte
+// stores that each touch a different sector).
+constexpr int kFillWarps = 4;
+constexpr int kRing = 256;  // entries per member ring: < 36 left after a flush + <= 128 new ones per step
+template <typename T>
+__global__ void __launch_bounds__(kFillWarps * 32)
+sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
+                         const unsigned int* itemptr, const unsigned int* rowid, T* val, unsigned short* off16) {
+  __shared__ __align__(16) T ringv[kFillWarps][4][kRing];
+  __shared__ __align__(8) unsigned short ringo[kFillWarps][4][kRing];
+  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NI = rows_pad >> 2;
+  const long long gw = (long long)blockIdx.x * kFillWarps + wic;
+  if (gw >= (long long)nseg * NI) return;
+  const int seg = (int)(gw / NI), it = (int)(gw - (long long)seg * NI);
+  const unsigned int b = itemptr[(size_t)seg * (NI + 1) + it], e = itemptr[(size_t)seg * (NI + 1) + it + 1];
+  const unsigned int L = (e - b) >> 2;  // chunks per member
+  if (L == 0u) return;
+  unsigned int r[4], n[4] = {0u, 0u, 0u, 0u}, f[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int s_ = 0; s_ < 4; ++s_) r[s_] = rowid[(size_t)seg * rows_pad + 4 * it + s_];
+  const int g = lane >> 2, ms = lane & 3;  // flush role: chunk f + g of member ms
+  T (*rv)[kRing] = ringv[wic];
+  unsigned short (*ro)[kRing] = ringo[wic];
+  // writes chunk k of member ms (entries beyond the member's n are neutral padding)
+  auto put_chunk = [&](unsigned int k, unsigned int nm) {
+    T x[4]; unsigned short o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned int w = 4u * k + q;
+      const bool have = w < nm;
+      x[q] = have ? rv[ms][w & (kRing - 1)] : encode<T>(0.0, false);
+      o[q] = have ? ro[ms][w & (kRing - 1)] : (unsigned short)kZeroSlot;
+    }
+    const unsigned long long at = 4ull * (b + 4ull * k + ms);
+    Quad<T>::store(val + at, x);
+    *reinterpret_cast<uint2*>(off16 + at) = make_uint2((unsigned int)o[0] | ((unsigned int)o[1] << 16), (unsigned int)o[2] | ((unsigned int)o[3] << 16));
+  };
+  const int c0 = seg * W, c1 = min(m, c0 + W);
+  for (int j0 = c0; j0 < c1; j0 += 128) {
+    const int j = j0 + lane * 4;
+#pragma unroll
+    for (int s_ = 0; s_ < 4; ++s_) {
+      if (r[s_] >= (unsigned int)rows) continue;  // warp-uniform
+      T x[4];
+      load4<T>(M + (size_t)r[s_] * ld + j, x);  // j + 3 < ld: ld is a multiple of 128
+      unsigned int keep = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j + q >= c1) x[q] = encode<T>(0.0, false);
+        keep |= (!is_neutral<T>(x[q]) ? 1u : 0u) << q;
+      }
+      const unsigned int cnt = __popc(keep);
+      unsigned int pre = cnt;  // inclusive scan over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
+      }
+      const unsigned int total = __shfl_sync(0xffffffffu, pre, 31);
+      unsigned int w = n[s_] + (pre - cnt);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (keep & (1u << q)) { rv[s_][w & (kRing - 1)] = x[q]; ro[s_][w & (kRing - 1)] = (unsigned short)(8 * (j + q - c0)); ++w; }
+      n[s_] += total;
+    }
+    __syncwarp();
+    // flush 8 complete chunks of every member that has them (members of an item have almost the same length:
+    // usually all four flush together and the store is one contiguous 512-byte run)
+    for (;;) {
+      const unsigned int nm = ms == 0 ? n[0] : ms == 1 ? n[1] : ms == 2 ? n[2] : n[3];
+      const unsigned int fm = ms == 0 ? f[0] : ms == 1 ? f[1] : ms == 2 ? f[2] : f[3];
+      const bool can = (nm >> 2) >= fm + 8u;
+      const unsigned int vote = __ballot_sync(0xffffffffu, can);
+      if (vote == 0u) break;
+      if (can) put_chunk(fm + g, nm);
+#pragma unroll
+      for (int s_ = 0; s_ < 4; ++s_) if (vote & (1u << s_)) f[s_] += 8u;  // lanes 0..3 are (g = 0, member s_)
+    }
+    __syncwarp();
+  }
+  // the rest of every member: remaining chunks, the partial one, then padding up to the item's length
+  {
+    const unsigned int nm = ms == 0 ? n[0] : ms == 1 ? n[1] : ms == 2 ? n[2] : n[3];
+    const unsigned int fm = ms == 0 ? f[0] : ms == 1 ? f[1] : ms == 2 ? f[2] : f[3];
+    for (unsigned int k = fm + g; k < L; k += 8u) put_chunk(k, nm);
   }
 }
 
