@@ -1,12 +1,4 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v3.json 2>gpurun_out/v3.err
-CLP_FILL_ITEMS=0 CLP_FUSE_COUNT=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v3_old.json 2>gpurun_out/v3_old.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_r01g.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-python - <<'PY'
-import json,glob
-for n in ["gpurun_out/v3.json","gpurun_out/v3_old.json"]:
-    try:
-        j=json.loads(open(n).read().strip().splitlines()[-1])
-        print(n,"value %.0f"%j["value"],"ms %.2f"%j["ms_per_step"],"e2e %.0f"%j["e2e"]["value"],"kernel %.2f"%j["config"].get("solver_kernel_ms"),{k:round(v,2) for k,v in j["config"].get("solver_phase_ms").items()},"mv %.3f"%j["config"]["matvec_alone_frac"],"roof %.3f"%j["roofline"]["frac"])
-    except Exception as e: print(n,"ERR",e)
-PY
+run() { n=$1; tag=$2; shift 2; env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 --no-config4 > gpurun_out/bench_$tag.log 2>&1; echo "$tag rc=$?"; grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*\|"solver_kernel_ms": [0-9.]*\|"solver_phase_ms": {[^}]*}' gpurun_out/bench_$tag.log | tr '\n' ' '; echo; }
+run 8 n8 X=1
+run 8 n8c3 CLP_CTAS_PER_SM=3
+run 4 n4 X=1
