@@ -111,7 +111,7 @@ struct clp_handle_s {
                           //            3 compact rows, 4 auto (compact rows when the graph is sparse enough, else 2 / 0)
   int dense_mode_eff = 2; // effective, decided when the matrix is finalised
   // compact-row copy (clp_sparse.cuh)
-  DevBuf sp_val, sp_col, sp_ptr4, sp_part, sp_item, sp_rowid, sp_rank;  // sp_ptr4: chunk counts per (segment, row)
+  DevBuf sp_val, sp_col, sp_ptr4, sp_part, sp_item, sp_rowid, sp_rank;  // sp_ptr4: kept entries per (segment, row)
   unsigned long long sp_nnz = 0, sp_nnz_real = 0;
   SparseView sp{};
   Plan2 plan2{};
@@ -743,7 +743,7 @@ int clp_destroy(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r)
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
-  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->F12, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->parts, &h->small,
+  for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->F12, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->sp_part, &h->sp_item, &h->sp_rowid, &h->sp_rank, &h->parts, &h->small,
                     &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
