@@ -339,9 +339,10 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps},
-        # kernels of this repository launched per step: gather_endpoints + score_tile + solver, plus the seven
-        # kernels that build the compact copy (count, sort, item lengths, 2 x scan, fill, partition) in mode 3
-        "gpu_launches": (10 if mode == 3 else 3) * args.steps,
+        # kernels of this repository launched per step: gather_endpoints + score_tile + solver, plus the kernels that
+        # build the compact copy in mode 3 (sort, item lengths, 2 x scan, fill, partition; + the counting pass when
+        # the scoring kernel does not produce the counts itself) -- see profiles/r01g_launches_bench_c2.csv
+        "gpu_launches": ((9 if FUSED_COUNT else 10) if mode == 3 else 3) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": "solver_kernel<float,%d> (persistent; %d passes over the matrix per launch)"
@@ -350,6 +351,9 @@ def run_ours(args):
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
+
+
+FUSED_COUNT = os.environ.get("CLP_FUSE_COUNT", "1") != "0" and os.environ.get("CLP_SCORE_FILTER", "1") != "0"
 
 
 def main():

@@ -297,7 +297,7 @@ def run_bench(args, METRIC, UNIT):
             "clocks": clocks,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(m * 8 + 320),
                     "note": "N>1: inputs replicated in HBM on every rank; result D2H inside the timed region"},
-            "gpu_launches": (10 if main["mode"] == 3 else 3) * args.steps * world,  # per rank: gather, score, solver (+7 building the compact copy)
+            "gpu_launches": (9 if main["mode"] == 3 else 3) * args.steps * world,  # per rank: gather, score, solver (+6 building the compact copy)
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "kernel": "solver_kernel<float>, per GPU", "peak_source": peak_src},
         }
