@@ -3,6 +3,8 @@
 //   K1  score_tile_kernel     scorePairwiseConsistency + invariants   (ref clipper.cpp:21-65,
 //                             euclidean_distance.cpp:13-31, pointnormal_distance.cpp:13-35)
 //   K2  matvec_*              penalised mat-vec  Mhat v, Chat v       (ref clipper.cpp:194-271)
+//                             other sweeps of the same matrix: clp_dense2.cuh (column stripes, upper triangle
+//                             two-sided), clp_sparse.cuh (compact sliced-ELL copy: the default when sparse)
 //   K3-K5 solver_kernel       whole findDenseClique() as ONE persistent cooperative kernel:
 //                             step/projection, objective, backtracking line search, penalty
 //                             ramp, all decided on the device            (ref clipper.cpp:172-283)

@@ -180,8 +180,9 @@ int clp_set_ctas_per_sm(clp_handle h, int n);
 /* How the solver / mat-vec sweep the matrix (the dense store always exists; getters read it):
  *   4 (default) auto: 3 when the graph is sparse enough for the compact copy to move fewer bytes than the
  *     best dense sweep (x0.8), else 2 on an unsharded handle / 0 on a sharded one;
- *   3: compact rows -- after the dense build the non-neutral entries of every row are packed in column
- *     order as (fp32 value, 16-bit column): 6 bytes per kept entry per objective evaluation;
+ *   3: compact copy -- after the dense build the non-neutral entries are packed as (fp32 value, 16-bit column
+ *     offset) into a sliced-ELL layout (rows sorted by length inside every column segment, four at a time,
+ *     interleaved in 4-entry chunks): 6 bytes per kept entry per objective evaluation;
  *   2: column stripes, ONLY the upper triangle is read and every element is applied two-sidedly in-tile
  *     -> ~2 m^2 bytes per objective evaluation (fp32 storage), single GPU;
  *   1: column stripes, full matrix (4 m^2 bytes);
