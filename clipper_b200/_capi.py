@@ -24,7 +24,7 @@ SYMBOLS = [
     "clp_solve", "clp_solve_dev", "clp_matvec", "clp_matvec_dev",
     "clp_k2ij", "clp_create_all_to_all", "clp_find_k_largest", "clp_find_above", "clp_dsd_dense",
     "clp_shard_config", "clp_shard_rows", "clp_shard_export", "clp_shard_import", "clp_shard_blob_bytes",
-    "clp_set_ctas_per_sm", "clp_set_dense_mode", "clp_get_dense_mode", "clp_sparse_info",
+    "clp_set_ctas_per_sm", "clp_set_grid_cap", "clp_set_dense_mode", "clp_get_dense_mode", "clp_sparse_info",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
     L.clp_shard_import.argtypes = [vp, vp, i64, C.c_int]
     L.clp_shard_rows.argtypes = [i64, C.c_int, C.c_int, lp, lp]; L.clp_shard_rows.restype = None
     L.clp_set_ctas_per_sm.argtypes = [vp, C.c_int]
+    L.clp_set_grid_cap.argtypes = [vp, C.c_int]
     L.clp_set_dense_mode.argtypes = [vp, C.c_int]
     L.clp_get_dense_mode.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.clp_sparse_info.argtypes = [vp, lp, lp]

@@ -299,6 +299,10 @@ class CLIPPER:
         """4 (default) auto; 3 compact rows; 2 upper triangle read once, two-sided update; 1 stripes/full; 0 segments"""
         _capi.check(self._h, self._lib.clp_set_dense_mode(self._h, int(mode)))
 
+    def set_grid_cap(self, n_ctas):
+        """at most n_ctas CTAs in this object's persistent kernels (0 = every SM); see clipper_b200/batch.py"""
+        _capi.check(self._h, self._lib.clp_set_grid_cap(self._h, int(n_ctas)))
+
     def dense_mode(self):
         """effective sweep mode of the current problem (sharded handles fall back from 2 to 1)"""
         a, b = C.c_int(), C.c_int()

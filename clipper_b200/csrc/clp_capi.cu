@@ -63,6 +63,8 @@ struct clp_handle_s {
   int head_kb = env_int("CLP_HEAD_KB", 0);       // compact sweep: KB per CTA prefetched into L2 during the sync steps
   int head_where = env_int("CLP_HEAD_WHERE", 1);
   int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? ctas_sparse : ctas_per_sm); }
+  int grid_cap = 0;          // > 0: at most this many CTAs in the persistent kernels (clp_set_grid_cap)
+  int grid_for(int ctas) const { const int g = sm_count * ctas; return grid_cap > 0 ? std::min(g, grid_cap) : g; }
 
   // sharding (row block [row0,row0+rows) of the m x m matrix lives here)
   int rank = 0, world = 1;
@@ -335,12 +337,12 @@ int set_plan_for(clp_handle h, int mode) {
     // more than 2 CTAs/SM only pay off when every CTA still gets several 32-row tiles; measured at m=20000:
     // 1 GPU (625 tiles) 3 > 2 CTAs/SM, 8 GPUs (79 tiles per shard) 2 > 3 > 1
     while (ctas > 2) {
-      const Plan pc = make_plan(h->m, h->rows_pad, h->sm_count * ctas);
+      const Plan pc = make_plan(h->m, h->rows_pad, h->grid_for(ctas));
       if (pc.NRT >= 4 * pc.RG) break;
       --ctas;
     }
   }
-  h->plan = make_plan(h->m, h->rows_pad, h->sm_count * ctas);
+  h->plan = make_plan(h->m, h->rows_pad, h->grid_for(ctas));
   CLP_CUDA(h, h->parts.ensure((size_t)2 * h->plan.NSEG * h->rows_pad * sizeof(double)));
   CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * h->plan.G * kRedVals) * sizeof(double)));
   return CLP_OK;
@@ -374,7 +376,7 @@ int ensure_matrix(clp_handle h, long long m) {
   h->ld = round_up(m, 128);
   h->mpad = round_up(m, 128);
   CLP_CUDA(h, h->Mbuf.ensure((size_t)h->rows_pad * (size_t)h->ld * h->esize()));
-  h->plan = make_plan(m, h->rows_pad, h->sm_count * h->ctas_for(h->dense_mode == 3 || h->dense_mode == 4 ? 3 : h->dense_mode));
+  h->plan = make_plan(m, h->rows_pad, h->grid_for(h->ctas_for(h->dense_mode == 3 || h->dense_mode == 4 ? 3 : h->dense_mode)));
   // workspace
   CLP_CUDA(h, h->vecs.ensure((size_t)V_SLOTS * h->mpad * sizeof(double)));
   {
@@ -1090,6 +1092,17 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
     }
   }
   h->shard_ready = true;
+  return CLP_OK;
+}
+
+int clp_set_grid_cap(clp_handle h, int n_ctas) {
+  if (!h || n_ctas < 0) return fail(h, CLP_ERR_INVALID, "grid cap must be >= 0 (0 = whole GPU)");
+  h->grid_cap = n_ctas;
+  if (h->m > 0) {
+    CLP_CUDA(h, cudaSetDevice(h->device));
+    if (h->has_matrix) { if (int rc = finalize_matrix(h)) return rc; }
+    else { if (int rc = set_plan_for(h, h->dense_mode == 3 || h->dense_mode == 4 ? 3 : h->dense_mode)) return rc; }
+  }
   return CLP_OK;
 }
 

@@ -482,19 +482,19 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
         if (lane == 0 && vote) atomicAdd(a.cnt + (size_t)((blockIdx.y * kRowTile) / a.W) * (a.rows_pad + 1) + j, (unsigned int)__popc(vote));
       }
     }
-    return;
-  }
-  // ... and the mirror image: column j of this thread's 4 rows is 4 consecutive elements of row j
+  } else {
+    // ... and the mirror image: column j of this thread's 4 rows is 4 consecutive elements of row j
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int j = c0 + e;
-    if (j >= a.rows_pad) continue;
-    T col[4] = {out[0][e], out[1][e], out[2][e], out[3][e]};
-    if (r0 + 3 < j && r0 + 3 < a.ld) Quad<T>::store(Mbase + (size_t)j * a.ld + r0, col);
-    else {
+    for (int e = 0; e < 4; ++e) {
+      const int j = c0 + e;
+      if (j >= a.rows_pad) continue;
+      T col[4] = {out[0][e], out[1][e], out[2][e], out[3][e]};
+      if (r0 + 3 < j && r0 + 3 < a.ld) Quad<T>::store(Mbase + (size_t)j * a.ld + r0, col);
+      else {
 #pragma unroll
-      for (int q = 0; q < kRowsPerWarp; ++q)
-        if (r0 + q < j && r0 + q < a.ld) Mbase[(size_t)j * a.ld + r0 + q] = col[q];
+        for (int q = 0; q < kRowsPerWarp; ++q)
+          if (r0 + q < j && r0 + q < a.ld) Mbase[(size_t)j * a.ld + r0 + q] = col[q];
+      }
     }
   }
 }

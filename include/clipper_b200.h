@@ -177,6 +177,12 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
  * compact-row sweep). 1 lets two shards share one GPU, which is how the sharded path is exercised on
  * a single-GPU box. */
 int clp_set_ctas_per_sm(clp_handle h, int n);
+/* Cap on the TOTAL number of CTAs of the persistent solver / mat-vec kernels of this handle (0 = no cap: every
+ * SM). A small problem (the reference's own use case is m <= 2000, benchmarks/main.cpp:206) cannot
+ * fill 148 SMs and pays for device-wide barriers between hundreds of CTAs; with a cap of a few CTAs per handle,
+ * many handles -- one per host thread, each on its own stream, like independent clipper::CLIPPER objects -- solve
+ * side by side on disjoint SMs (clipper_b200/batch.py). */
+int clp_set_grid_cap(clp_handle h, int n_ctas);
 /* How the solver / mat-vec sweep the matrix (the dense store always exists; getters read it):
  *   4 (default) auto: 3 when the graph is sparse enough for the compact copy to move fewer bytes than the
  *     best dense sweep (x0.8), else 2 on an unsharded handle / 0 on a sharded one;
