@@ -62,7 +62,7 @@ struct clp_handle_s {
   int ctas_cap = 3;          // user cap (clp_set_ctas_per_sm)
   int head_kb = env_int("CLP_HEAD_KB", 0);       // compact sweep: KB per CTA prefetched into L2 during the sync steps
   int head_where = env_int("CLP_HEAD_WHERE", 1);
-  int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? ctas_sparse : ctas_per_sm); }
+  int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? (ring_ctas > 0 ? ring_ctas : ctas_sparse) : ctas_per_sm); }
   int grid_cap = 0;          // > 0: at most this many CTAs in the persistent kernels (clp_set_grid_cap)
   int grid_for(int ctas) const { const int g = sm_count * ctas; return grid_cap > 0 ? std::min(g, grid_cap) : g; }
 
@@ -89,6 +89,8 @@ struct clp_handle_s {
   DevBuf A_dev;                 // int32 [2m]
   DevBuf E1, E2, D1dev, D2dev, F12;  // F12: fp32 positions of both endpoints (screening pass of the scoring kernel)
   int score_filter = env_int("CLP_SCORE_FILTER", 1);
+  int ring_depth = env_int("CLP_SPARSE_RING", 0);   // EXPERIMENTAL cp.async ring sweep of the compact copy: stages (0 = off)
+  int ring_ctas = 0;                                // CTAs/SM the ring instance reaches with its dynamic shared memory
   int fuse_count = env_int("CLP_FUSE_COUNT", 1);  // scoring kernel counts the kept entries (skips sparse_count_kernel)
   bool counts_fused = false;                        // sp_ptr4 already holds the counts of the current matrix
   int fill_items = env_int("CLP_FILL_ITEMS", 1);  // compact copy written item-wise (coalesced) instead of row-wise
@@ -554,6 +556,11 @@ int matvec_enqueue(clp_handle h, const double* v_dev, double d, double* y_dev, d
 template <typename T>
 cudaError_t launch_solver(clp_handle h, SolverArgs& a) {
   void* args[] = {&a};
+  if constexpr (sizeof(T) == 4) {
+    if (h->dense_mode_eff == 3 && h->ring_ctas > 0)  // experimental ring sweep (clp_sparse.cuh, sparse_phase_ring)
+      return cudaLaunchCooperativeKernel((const void*)solver_kernel<T, 5>, dim3(h->plan.G), dim3(kThreads), args,
+                                         ring_bytes_per_cta(a.ring_depth), h->stream);
+  }
   const void* fn = h->dense_mode_eff == 3 ? (const void*)solver_kernel<T, 3>
                  : h->dense_mode_eff == 2 ? (const void*)solver_kernel<T, 2>
                  : h->dense_mode_eff == 1 ? (const void*)solver_kernel<T, 1> : (const void*)solver_kernel<T, 0>;
@@ -589,6 +596,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   a.out = reinterpret_cast<SolverOut*>(h->result.p);
   a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
   a.rank = h->rank; a.world = h->world; a.seq0 = h->seq;
+  a.ring_depth = h->ring_ctas > 0 ? h->ring_depth : 0;
   a.comm = h->comm.as<CommBlock>();
   for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
   if (h->world > 1) {
@@ -734,6 +742,17 @@ int clp_create(int device, int storage, clp_handle* out) {
   if (e != cudaSuccess || occ < 1 || occ3 < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
   h->ctas_per_sm = std::min(occ, 2);
   h->ctas_sparse = std::min(occ3, 3);
+  if (h->ring_depth > 0 && storage == CLP_STORE_F32) {  // experimental ring sweep: needs opt-in dynamic shared memory
+    h->ring_depth = std::min(std::max(h->ring_depth, 2), kRingMaxDepth);
+    const size_t rb = ring_bytes_per_cta(h->ring_depth);
+    int occ5 = 0;
+    e = cudaFuncSetAttribute(solver_kernel<float, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ5, solver_kernel<float, 5>, kThreads, rb);
+    if (e != cudaSuccess || occ5 < 1) return bail("ring sweep: dynamic shared memory / occupancy", e);
+    h->ring_ctas = std::min(occ5, 3);
+  } else {
+    h->ring_depth = 0;
+  }
 
   *out = h;
   return CLP_OK;

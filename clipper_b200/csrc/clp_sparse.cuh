@@ -525,4 +525,168 @@ __device__ void sparse_phase(const MatView& mv, const Plan& p, const StageArgs& 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL variant of the sweep (solver_kernel<T, 5>, CLP_SPARSE_RING=<depth>; not validated on hardware in
+// round 1): the rounds travel through a lane-private ring in dynamic shared memory filled
+// with cp.async, so the bytes in flight per lane are (depth - 1) rounds and cost no registers.  Every lane copies
+// its own chunks and later reads back only what it copied itself: cp.async.wait_group is the only ordering the
+// data needs.  Per stage a few words of metadata written by the warp tell the consumer which item the round
+// belongs to.  The arithmetic is sell_apply's with kRingUnroll chunks per round.
+constexpr int kRingUnroll = 2;   // chunks per lane and round
+constexpr int kRingMaxDepth = 8;
+__host__ __device__ constexpr size_t ring_bytes_per_cta(int depth) {
+  return (size_t)kWarps * depth * (kRingUnroll * 32 * 24 + 32);  // chunks (16 + 8 B per lane) + 8 words of metadata
+}
+
+__device__ __forceinline__ unsigned char* dynamic_smem() {
+  extern __shared__ __align__(16) unsigned char clp_dyn_smem[];
+  return clp_dyn_smem;
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n groups still in flight
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+
+template <typename T, bool PLAIN_ONLY>
+__device__ void sparse_phase_ring(const MatView& mv, const Plan& p, const StageArgs& st, const SparseView& sp,
+                                  double* partM, double* partC, double* vs, double* red_smem, int ring_depth) {
+  static_assert(sizeof(T) == 4, "the ring is laid out for fp32 storage");
+  __shared__ int next_item;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NI = sp.rows_pad >> 2;
+  const int D = min(max(ring_depth, 2), kRingMaxDepth);
+  // this warp's part of the ring: values [D][U][32] x 16 B, offsets [D][U][32] x 8 B, metadata [D][8] words
+  unsigned char* base = dynamic_smem() + (size_t)warp * D * (kRingUnroll * 32 * 24 + 32);
+  T (*rv)[4] = reinterpret_cast<T (*)[4]>(base);                                          // chunk values (fp32 only)
+  uint2* ro = reinterpret_cast<uint2*>(base + (size_t)D * kRingUnroll * 32 * 16);          // chunk offsets
+  unsigned int* meta = reinterpret_cast<unsigned int*>(base + (size_t)D * kRingUnroll * 32 * 24);  // [D][8]
+  const T* val = reinterpret_cast<const T*>(sp.val);
+
+  unsigned int g = sp.cta_first[blockIdx.x];
+  const unsigned int gend = sp.cta_first[blockIdx.x + 1];
+  if (threadIdx.x == 0) vs[kSegMax] = 0.0;
+  for (int seg = (int)(g / (unsigned int)NI); g < gend; ++seg) {
+    const int it0 = (int)(g - (unsigned int)seg * NI);
+    const int it1 = (int)min(gend - (unsigned int)seg * NI, (unsigned int)NI);
+    if (threadIdx.x == 0) next_item = it0 + kWarps;
+    stage_segment<double>(st, p, mv.m, seg, it0 == 0, vs, red_smem);
+    const unsigned int* ipseg = sp.itemptr + (size_t)seg * (NI + 1);
+    const unsigned int* rowseg = sp.rowid + (size_t)seg * sp.rows_pad;
+    auto fetch = [&](int it) -> unsigned int {  // lanes 0,1: chunk range of the item; lanes 2..5: its member rows
+      if (it >= it1) return 0u;
+      if (lane < 2) return ipseg[it + lane];
+      if (lane < 6) return rowseg[4 * it + lane - 2];
+      return 0u;
+    };
+    int it = it0 + warp;
+    if (it < it1) {
+      // ---- producer state (warp-uniform): the item being copied and the descriptor of the one after it
+      unsigned int q0 = fetch(it);
+      int itn = 0;
+      if (lane == 0) itn = atomicAdd(&next_item, 1);
+      itn = __shfl_sync(0xffffffffu, itn, 0);
+      unsigned int q1 = fetch(itn);
+      unsigned int pj = __shfl_sync(0xffffffffu, q0, 0);     // first chunk of the next round to copy
+      unsigned int pe = __shfl_sync(0xffffffffu, q0, 1);     // end of the item being copied
+      unsigned int prow = __shfl_sync(0xffffffffu, q0, 2 + (lane & 3));
+      bool pdone = false;                                     // no item left to copy
+      // copies one round into stage s (or marks the stage "end of stream") and commits the group
+      auto produce = [&](int s) {
+        unsigned int flag = 2u;  // 0: inside an item, 1: last round of its item, 2: end of stream
+        if (!pdone) {
+          const bool last = pj + 32u * kRingUnroll >= pe;
+          flag = last ? 1u : 0u;
+#pragma unroll
+          for (int u = 0; u < kRingUnroll; ++u) {
+            const unsigned int c = pj + lane + 32u * u;
+            T* dv = rv[(s * kRingUnroll + u) * 32 + lane];
+            uint2* dof = ro + (s * kRingUnroll + u) * 32 + lane;
+            if (c < pe) { cp_async_16(dv, val + 4ull * c); cp_async_8(dof, sp.off16 + 4ull * c); }
+            else {
+              dv[0] = dv[1] = dv[2] = dv[3] = encode<T>(0.0, false);
+              *dof = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16));
+            }
+          }
+          if (lane < 4) meta[s * 8 + lane] = prow;
+          if (last) {  // move on to the next item
+            if (itn >= it1) pdone = true;
+            else {
+              pj = __shfl_sync(0xffffffffu, q1, 0); pe = __shfl_sync(0xffffffffu, q1, 1);
+              prow = __shfl_sync(0xffffffffu, q1, 2 + (lane & 3));
+              if (lane == 0) itn = atomicAdd(&next_item, 1);
+              itn = __shfl_sync(0xffffffffu, itn, 0);
+              q1 = fetch(itn);
+            }
+          } else pj += 32u * kRingUnroll;
+        }
+        if (lane == 4) meta[s * 8 + 4] = flag;
+        cp_async_commit();
+      };
+      for (int s = 0; s < D - 1; ++s) produce(s);
+      double aM[2] = {0.0, 0.0}, aC[2] = {0.0, 0.0};
+      int sc = 0, sprod = D - 1;              // stage consumed now / stage refilled now (= consumed in the previous trip)
+      for (;; sc = (sc + 1 == D) ? 0 : sc + 1, sprod = (sprod + 1 == D) ? 0 : sprod + 1) {
+        produce(sprod);
+        cp_async_wait_pending(D - 1);         // the group of round r has landed
+        __syncwarp();                         // metadata of stage sc (written by lanes 0..4) visible to all lanes
+        const unsigned int flag = meta[sc * 8 + 4];
+        if (flag == 2u) break;
+#pragma unroll
+        for (int u = 0; u < kRingUnroll; ++u) {
+          const float4 x = *reinterpret_cast<const float4*>(rv[(sc * kRingUnroll + u) * 32 + lane]);
+          const uint2 k = ro[(sc * kRingUnroll + u) * 32 + lane];
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double v = vs_at(vs, off_of(k, q));
+            if (PLAIN_ONLY || sp.plain) {
+              aM[u & 1] = fma((double)xs[q], v, aM[u & 1]);
+              aC[u & 1] += v;
+            } else {
+              double dummyM = 0.0, dummyC = 0.0;
+              apply_elem<false>(xs[q], v, 0.0, aM[u & 1], aC[u & 1], dummyM, dummyC);
+            }
+          }
+        }
+        if (flag == 1u) {
+          double accM = aM[0] + aM[1], accC = aC[0] + aC[1];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            accM += __shfl_xor_sync(0xffffffffu, accM, o);
+            accC += __shfl_xor_sync(0xffffffffu, accC, o);
+          }
+          if (lane < 4) {
+            const unsigned int row = meta[sc * 8 + lane];
+            partM[(size_t)seg * mv.rows_pad + row] = accM;
+            partC[(size_t)seg * mv.rows_pad + row] = accC;
+          }
+          aM[0] = aM[1] = aC[0] = aC[1] = 0.0;
+        }
+        __syncwarp();                         // stage sc may be overwritten by the next trip's produce()
+      }
+      cp_async_wait_pending(0);
+    }
+    __syncthreads();  // vs, next_item and the ring are re-used by the next segment pass
+    g = (unsigned int)(seg + 1) * NI;
+  }
+}
+
 }  // namespace clp

@@ -59,3 +59,20 @@ def test_batch_equals_one_by_one(built):
         assert g.nodes == w.nodes
         assert abs(g.score - w.score) <= 1e-9 * max(abs(w.score), 1.0)
         assert g.associations.shape == (len(w.nodes), 2)
+
+
+@pytest.mark.parametrize("depth", [2, 3, 4, 6])
+def test_ring_sweep_matches_the_default_sweep(built, depth, monkeypatch):
+    """solver_kernel<float,5> (cp.async ring, CLP_SPARSE_RING=<depth>, read when the handle is created) against the
+    default compact sweep: same decisions, same inlier set, objective to rounding"""
+    p = _problem(3000, 21)
+    ref = _clipper(0, 3); ref.score_pairwise_consistency(p["D1"], p["D2"], p["A"]); ref.solve(p["u0"])
+    r = ref.get_solution()
+    monkeypatch.setenv("CLP_SPARSE_RING", str(depth))
+    c = _clipper(0, 3)
+    monkeypatch.delenv("CLP_SPARSE_RING")
+    c.score_pairwise_consistency(p["D1"], p["D2"], p["A"]); c.solve(p["u0"])
+    s = c.get_solution()
+    assert s.nodes == r.nodes and s.ifinal == r.ifinal and s.n_evals == r.n_evals
+    assert abs(s.score - r.score) <= 1e-10 * abs(r.score)
+    assert np.allclose(s.u, r.u, rtol=0, atol=1e-11)
