@@ -495,3 +495,69 @@ def test_compact_rows_keep_every_non_neutral_entry(clp, orc, storage):
     # switching the sweep on an existing matrix re-finalises it
     c.set_dense_mode(0); y0, _, _ = c.matvec(v, 1.1)
     assert np.abs(y0 - y).max() <= 1e-12 * np.abs(y).max()
+
+
+# ------------------------------------------------------------------------------------------
+# committed golden files (tests/golden/*.npz: seeded inputs + the oracle's outputs, frozen by
+# tests/test_oracle_golden.py::test_oracle_reproduces_golden_files)
+# ------------------------------------------------------------------------------------------
+def _golden_cases():
+    import glob
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(here, "*.npz")))
+
+
+@pytest.mark.parametrize("storage", [0, 1])
+@pytest.mark.parametrize("name", _golden_cases())
+def test_cuda_path_against_golden_files(clp, name, storage):
+    import os
+    import sys
+    import scipy.sparse as sp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    g = make_golden.load(name)
+    m = g["A"].shape[0]
+    if g["kind"] == "euclidean":
+        c = make_euclid(clp, storage=storage, **g["params"]); ulps = 4
+    else:
+        c = make_pn(clp, storage=storage, **g["params"]); ulps = 2048
+    c.score_pairwise_consistency(g["D1"], g["D2"], g["A"])
+    U = sp.csc_matrix((g["M_val"], g["M_rowidx"], g["M_colptr"]), shape=(m, m)).toarray()
+    Mo = U + U.T + np.eye(m)
+    assert_affinity_close(c.get_affinity_matrix(), Mo, storage, ulps64=ulps)
+    y, Mv, Cv = c.matvec(g["v"], float(g["d"]))
+    tol = (1e-12 if g["kind"] == "euclidean" else 1e-9) if storage == 1 else 1e-5
+    assert np.abs(Mv - g["Mv"]).max() <= tol * np.abs(g["Mv"]).max()
+    assert np.abs(Cv - g["Cv"]).max() <= 1e-12 * np.abs(g["Cv"]).max()
+    assert np.abs(y - g["gradf"]).max() <= tol * np.abs(g["gradf"]).max()
+    c.solve(g["u0"]); s = c.get_solution()
+    assert sorted(s.nodes) == sorted(g["nodes"].tolist())
+    assert abs(s.score - float(g["score"])) <= (1e-9 if storage == 1 else 1e-5) * abs(float(g["score"]))
+    assert np.abs(s.u - g["u"]).max() <= ((1e-8 if g["kind"] == "euclidean" else 1e-6) if storage == 1 else 1e-4)
+    if g["kind"] == "euclidean":  # PointNormal values carry the acos difference (<= 2048 ulp): only the answer is pinned
+        assert s.ifinal == int(g["ifinal"])
+    if storage == 1 and g["kind"] == "euclidean":
+        assert s.n_evals == int(g["n_evals"]) and s.n_inner == int(g["n_inner"])
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("mindist", [0.0, 0.2])
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (1e3, 0.0), (1e-3, 0.0), (1.0, 1e4)])
+def test_screened_scoring_fp32_store(clp, orc, d, mindist, scale, shift):
+    """default storage (fp32): the fp32-screened scoring kernel (compile-time d = 2, 3) must give the oracle's
+    pattern exactly -- with mindist, at other coordinate scales and far from the origin (where the screening margin
+    1024 * 2^-24 * R grows past epsilon and every pair takes the exact path)"""
+    rng = np.random.default_rng(100 * d + int(mindist * 10) + int(np.log10(scale)) + int(shift > 0))
+    n, m = 60, 333
+    P = rng.random((d, n))
+    D1 = np.asfortranarray(scale * P + shift); D2 = np.asfortranarray(scale * (P + 0.002 * rng.standard_normal((d, n))) + shift)
+    A = np.stack([rng.integers(0, n, m), rng.integers(0, n, m)], axis=1).astype(np.int32)
+    kw = dict(sigma=0.02 * scale, epsilon=0.05 * scale, mindist=mindist * scale)
+    c = make_euclid(clp, storage=0, **kw)
+    c.score_pairwise_consistency(D1, D2, A)
+    o = orc.Oracle(); o.score_euclidean(D1, D2, A, **kw)
+    assert_affinity_close(c.get_affinity_matrix(), o.get_affinity_matrix(), 0)
+    nM, nC = c.count_nonzeros()
+    assert nM == o.nnz(0) and nC == o.nnz(1)
+    assert c.sparse_info()[0] in (0, 2 * o.nnz(0))  # kept entries of the compact copy (0: a dense sweep was chosen)

@@ -114,3 +114,37 @@ def test_mindist():
     ai, aj = np.array([0.0, 0, 0]), np.array([0.05, 0, 0])
     assert orc.euclidean(ai, aj, ai, aj, mindist=0.1) == 0.0
     assert orc.euclidean(ai, aj, ai, aj, mindist=0.0) == 1.0
+
+
+# ------------------------------------------------------------------------------------------
+# committed golden files (tests/golden/*.npz, written by tests/golden/make_golden.py)
+# ------------------------------------------------------------------------------------------
+def _golden_cases():
+    import glob
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(here, "*.npz")))
+
+
+@pytest.mark.parametrize("name", _golden_cases())
+def test_oracle_reproduces_golden_files(name):
+    """the oracle is the pin for everything the reference's tests do not observe (solver trajectory, mat-vec):
+    freeze it -- same inputs must give bit-identical scores, mat-vec, objective and iterate"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    from oracle.clipper_oracle import Oracle
+    g = make_golden.load(name)
+    o = Oracle()
+    if g["kind"] == "euclidean":
+        o.score_euclidean(g["D1"], g["D2"], g["A"], **g["params"])
+    else:
+        o.score_pointnormal(g["D1"], g["D2"], g["A"], **g["params"])
+    cp, ri, val = o.get_csc(0)
+    assert np.array_equal(cp, g["M_colptr"]) and np.array_equal(ri, g["M_rowidx"]) and np.array_equal(val, g["M_val"])
+    y, _ = o.gradf(g["v"], float(g["d"]))
+    assert np.array_equal(y, g["gradf"]) and np.array_equal(o.matvec(g["v"], 0), g["Mv"]) and np.array_equal(o.matvec(g["v"], 1), g["Cv"])
+    s = o.solve(g["u0"])
+    assert s.nodes.tolist() == g["nodes"].tolist() and s.score == float(g["score"]) and np.array_equal(s.u, g["u"])
+    assert (s.ifinal, s.n_evals, s.n_inner) == (int(g["ifinal"]), int(g["n_evals"]), int(g["n_inner"]))
