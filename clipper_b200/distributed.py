@@ -41,6 +41,40 @@ def partition_is_exact(m, world):
     return nxt == m
 
 
+def interleave_permutation(m, world):
+    """new_of_old[i]: deal the associations to the row shards round-robin (shard sizes as clp_shard_rows cuts them).
+    Row-count shards are not byte-balanced when dense rows cluster -- the benchmark generator puts the inlier
+    associations last (reference bm_utils.cpp:312-315,344): 1.144x the mean bytes on the last of 8 shards at
+    BASELINE config 2.  Scoring the permuted association list permutes M symmetrically; the solution of the
+    permuted problem maps back with unpermute_solution().  Host-side only; opt-in (CLP_SHARD_INTERLEAVE=1 in
+    bench.py --gpus N), not yet measured on hardware."""
+    bounds = [shard_rows(m, r, world) for r in range(world)]
+    # slot k of a shard with n rows is due at time (k + 0.5) / n: taking all slots in time order fills every shard
+    # at a rate proportional to its size, so any run of consecutive associations is spread evenly
+    due = np.concatenate([(np.arange(n) + 0.5) / max(n, 1) for _, n in bounds])
+    slot = np.concatenate([r0 + np.arange(n) for r0, n in bounds])
+    new_of_old = slot[np.argsort(due, kind="stable")].astype(np.int64)
+    return new_of_old
+
+
+def permute_problem(A, u0, new_of_old):
+    """association list and start vector in the permuted numbering"""
+    A = np.asarray(A); m = A.shape[0]
+    Ap = np.empty_like(A); Ap[new_of_old] = A
+    u0p = None
+    if u0 is not None:
+        u0p = np.empty(m, dtype=np.float64); u0p[new_of_old] = np.asarray(u0, dtype=np.float64)
+    return np.asfortranarray(Ap), u0p
+
+
+def unpermute_solution(nodes_new, u_new, new_of_old):
+    """node indices and iterate of the permuted problem in the caller's numbering (node order is kept)"""
+    old_of_new = np.empty_like(new_of_old); old_of_new[new_of_old] = np.arange(len(new_of_old))
+    nodes_old = old_of_new[np.asarray(nodes_new, dtype=np.int64)].astype(np.int32)
+    u_old = None if u_new is None else np.asarray(u_new)[new_of_old]
+    return nodes_old, u_old
+
+
 class ShardedCLIPPER(CLIPPER):
     """clipper::CLIPPER whose affinity matrix is row-sharded over the ranks of a process group.
     Every rank calls every method collectively with identical arguments."""
@@ -215,6 +249,8 @@ def run_bench(args, METRIC, UNIT):
     def one_workload(name, m_override, steps, warmup):
         prob = datagen.config_problem(name, m_override)
         cfg = prob["cfg"]; m = cfg["m"]
+        if os.environ.get("CLP_SHARD_INTERLEAVE") == "1":  # opt-in: byte-balance the shards (see interleave_permutation)
+            prob["A"], prob["u0"] = permute_problem(prob["A"], prob["u0"], interleave_permutation(m, world))
         ip = clipperpy.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = cfg["sigma"], cfg["epsilon"]
         clip = ShardedCLIPPER(clipperpy.invariants.EuclideanDistance(ip), clipperpy.Params())
         if os.environ.get("CLP_DENSE_MODE"):

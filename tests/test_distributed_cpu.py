@@ -74,3 +74,32 @@ def test_partition_exact_for_many_sizes(built):
             for r in range(world):
                 r0, n = cd.shard_rows(m, r, world)
                 assert r0 % 32 == 0  # shards never split a 32-row tile
+
+
+def test_interleaved_shards_same_answer_and_balanced(built):
+    """opt-in byte balancing of the row shards: dealing the associations round-robin is a bijection that keeps the
+    shard sizes, spreads a block of dense rows evenly, and -- solved by the oracle -- gives the same inlier set
+    once mapped back"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    from clipper_b200 import distributed as cd
+    from oracle.clipper_oracle import Oracle
+    for m, world in ((1000, 8), (333, 4), (20000, 8), (64, 2)):
+        p = cd.interleave_permutation(m, world)
+        assert sorted(p.tolist()) == list(range(m))
+        last = np.arange(m - m // 20, m)  # the generator's inlier block: the last 5 % of the associations
+        for r in range(world):
+            r0, n = cd.shard_rows(m, r, world)
+            got = int(((p[last] >= r0) & (p[last] < r0 + n)).sum())
+            assert abs(got - len(last) * n / m) <= 1.0 + 1e-9, (m, world, r, got)
+    g = make_golden.load("euclid_m300")
+    m = g["A"].shape[0]
+    p = cd.interleave_permutation(m, 4)
+    Ap, u0p = cd.permute_problem(g["A"], g["u0"], p)
+    o = Oracle(); o.score_euclidean(g["D1"], g["D2"], Ap, **g["params"])
+    s = o.solve(u0p)
+    nodes, u = cd.unpermute_solution(s.nodes, s.u, p)
+    assert sorted(nodes.tolist()) == sorted(g["nodes"].tolist())
+    assert abs(s.score - float(g["score"])) <= 1e-12 * float(g["score"])
+    assert np.allclose(u, g["u"], rtol=0, atol=1e-12)
