@@ -5,7 +5,7 @@
 # usage (single GPU):  gpurun --timeout 900 -- 'bash scripts/gpu_validate_experimental.sh'
 mkdir -p gpurun_out
 CLP_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_batch.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/exp_tests.log
-# multi-GPU (run under gpurun --gpus N): CLP_SHARD_INTERLEAVE=1 python -m torch.distributed.run ... bench.py --gpus N
+# multi-GPU (run under gpurun --gpus N): CLP_SHARD_INTERLEAVE=1 CLP_BENCH_E2E_MULTI=1 python -m torch.distributed.run ... bench.py --gpus N
 for d in 0 2 3 4 6; do
   CLP_SPARSE_RING=$d timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/exp_ring_$d.json 2> gpurun_out/exp_ring_$d.err
 done
