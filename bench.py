@@ -274,7 +274,7 @@ def run_ours(args):
     # strict upper triangle only (2 m^2) when every element is applied two-sidedly in-tile (mode 2)
     pass_bytes = (esz * m * m) if mode != 2 else (esz * m * (m - 1) // 2)
     nnz_kept = None
-    if mode == 3:  # compact rows: 6 B per kept entry + per-row offsets (clp_sparse_info)
+    if mode == 3:  # compact copy: 6 B per kept entry + item descriptors (clp_sparse_info)
         nnz_kept, pass_bytes = clip.sparse_info()
     alg_bytes = float(np.mean(n_matvec)) * pass_bytes
     kms = float(np.mean(kernel_ms))
@@ -328,7 +328,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (dense M = %.2f GB vs 126 MB L2)" % (esz * m * m / 1e9),
                    "dense_sweep": {0: "segments, full matrix (4 m^2 B/pass)", 1: "stripes, full matrix (4 m^2 B/pass)",
                                    2: "stripes, upper triangle read once, two-sided in-tile update (2 m^2 B/pass)",
-                                   3: "compact rows: (fp32 value, 16-bit column) per kept entry, 6 B/entry/pass"}[mode],
+                                   3: "compact sliced-ELL copy: (fp32 value, 16-bit column offset) per kept entry, 6 B/entry/pass"}[mode],
                    "kept_entries": nnz_kept, "dense_equivalent_gbs": float(np.mean(n_matvec)) * esz * m * m / (kms * 1e-3) / 1e9,
                    "algorithmic_bytes_per_pass": pass_bytes,
                    "evals_per_solve": float(np.mean(evals)), "matvec_per_solve": float(np.mean(n_matvec)),
