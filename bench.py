@@ -10,8 +10,10 @@ score the m x m consistency graph, then run the graduated projected-gradient sol
   value : m*K / device time, inputs (D1, D2, A, u0) already resident in HBM (clp_*_dev entry points)
   e2e   : the same through the host-pointer C-ABI calls (pinned host buffers in, Solution out),
           host<->device copies inside the timed region
-  roofline : solver kernel (the dominant launch): n_matvec * 4 m^2 algorithmic bytes / its CUDA-event
-             duration, against MEASURED_PEAKS.json's hbm_gbs
+  roofline : solver kernel (the dominant launch): passes over the matrix x algorithmic bytes of one pass of the sweep
+             in use (compact copy: 6 B per kept entry + item descriptors, clp_sparse_info; dense sweeps: 4 m^2, or
+             2 m^2 for the two-sided upper-triangle sweep) / its CUDA-event duration, against MEASURED_PEAKS.json's
+             hbm_gbs; the dense-equivalent figure (4 m^2 per pass) is reported beside it
   cpu_baseline / --impl reference : the CPU oracle (Eigen-free restatement of the reference; the
              reference cannot be built offline -- no Eigen) on this box's host cores.
 Prints exactly ONE JSON line on rank 0.
@@ -111,6 +113,14 @@ def oracle_step(prob, nthreads):
                 nnz=o.nnz(0))
 
 
+def workload_name(name, cfg):
+    """the SAME string in both arms (the driver compares the two lines' config)"""
+    if cfg["kind"] == "euclidean":
+        return "%s: synthetic EuclideanDistance m=%d, %d%% outliers, sigma=%g eps=%g" % (
+            name, cfg["m"], round(100 * cfg["rho"]), cfg["sigma"], cfg["epsilon"])
+    return "%s: synthetic PointNormalDistance m=%d, %d%% outliers" % (name, cfg["m"], round(100 * cfg["rho"]))
+
+
 def cpu_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -128,14 +138,11 @@ def run_reference(args):
         return
     from clipper_b200 import datagen
     cores = cpu_cores()
-    full_m = datagen.CONFIGS[args.workload]["m"]
-    # budget: keep (K+W) steps within ~4 minutes; ~17 s per full c2 step on 8 x 2.1 GHz cores
-    est_full = 17.0 * (full_m / 20000.0) ** 2
-    budget = 240.0
-    m_s = full_m
-    if est_full * args.steps > budget:
-        m_s = int(max(2000, (full_m * (budget / (est_full * args.steps)) ** 0.5) // 1000 * 1000))
-    prob = datagen.config_problem(args.workload, m_s)
+    # ALWAYS the GPU arm's configuration (same m, same seeded inputs): a ratio across two problem sizes is void.
+    # One full c2 step costs ~12 s on the GPU box's cores (scoring OpenMP 0.7 s + single-threaded solver 11.3 s),
+    # i.e. K = 20 steps take about 4 minutes; only the untimed warm-up steps run on a small instance.
+    prob = datagen.config_problem(args.workload, args.m)
+    m_s = prob["cfg"]["m"]
     warm = datagen.config_problem(args.workload, min(2000, m_s))
     for _ in range(args.warmup):
         oracle_step(warm, cores)  # warm-up on a small instance (thread pool, page cache)
@@ -147,17 +154,18 @@ def run_reference(args):
         ts.append(info["t_score"] + info["t_solve"])
     total = time.perf_counter() - t0
     value = m_s * args.steps / total
-    sample = "full %s problem, m=%d" % (args.workload, m_s) if m_s == full_m else \
-        "m=%d sample of %s (m=%d) to bound the run" % (m_s, args.workload, full_m)
+    sample = "full %s problem, m=%d, every step" % (args.workload, m_s)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: synthetic EuclideanDistance m=%d, 95%% outliers" % (args.workload, m_s),
-                   "t_score_s": info["t_score"], "t_solve_s": info["t_solve"], "evals": info["evals"]},
+        "config": {"workload": workload_name(args.workload, prob["cfg"]),
+                   "cloud": datagen.cloud_source(),
+                   "t_score_s": info["t_score"], "t_solve_s": info["t_solve"], "evals": info["evals"],
+                   "F": info["score"], "n_nodes": len(info["nodes"])},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + "; oracle restatement (Eigen/MKL unavailable offline): scoring OpenMP x%d, "
-                                            "solver 1 thread like the reference; warm-up on m=%d" % (cores, min(2000, m_s))},
+                                            "solver 1 thread like the reference; untimed warm-up on m=%d" % (cores, min(2000, m_s))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -323,8 +331,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 (f32 affinity storage, fp64 vectors/accumulators/decisions)", "data": "synthetic",
-        "config": {"workload": "%s: synthetic EuclideanDistance m=%d, 95%% outliers, sigma=%g eps=%g"
-                               % (args.workload, m, cfg["sigma"], cfg["epsilon"]),
+        "config": {"workload": workload_name(args.workload, cfg), "cloud": datagen.cloud_source(),
                    "l2": "inputs larger than L2 (dense M = %.2f GB vs 126 MB L2)" % (esz * m * m / 1e9),
                    "dense_sweep": {0: "segments, full matrix (4 m^2 B/pass)", 1: "stripes, full matrix (4 m^2 B/pass)",
                                    2: "stripes, upper triangle read once, two-sided in-tile update (2 m^2 B/pass)",

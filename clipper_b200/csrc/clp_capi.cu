@@ -93,6 +93,7 @@ struct clp_handle_s {
   int ring_ctas = 0;                                // CTAs/SM the ring instance reaches with its dynamic shared memory
   int fuse_count = env_int("CLP_FUSE_COUNT", 1);  // scoring kernel counts the kept entries (skips sparse_count_kernel)
   bool counts_fused = false;                        // sp_ptr4 already holds the counts of the current matrix
+  long long counts_m = 0; int counts_rows_pad = 0, counts_nseg = 0, counts_W = 0;  // ... which was this one
   int fill_items = env_int("CLP_FILL_ITEMS", 1);  // compact copy written item-wise (coalesced) instead of row-wise
 
   // solver workspace
@@ -260,7 +261,10 @@ int build_sparse(clp_handle h, bool force) {
   const Plan& p = h->plan;
   const int nseg = p.NSEG;
   const long long nptr = (long long)nseg * (h->rows_pad + 1);
-  const bool fused = h->counts_fused;  // counts produced by the scoring kernel (scored matrices are "plain")
+  // counts produced by the scoring kernel (scored matrices are "plain"): only trusted for the very matrix and
+  // segmentation they were counted for
+  const bool fused = h->counts_fused && h->counts_m == h->m && h->counts_rows_pad == h->rows_pad &&
+                     h->counts_nseg == nseg && h->counts_W == p.W;
   h->counts_fused = false;
   if (int rc = reset_sync(h)) return rc;
   SyncBlock* sb = h->sync.as<SyncBlock>();
@@ -472,7 +476,6 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
     CLP_CUDA(h, h->sp_ptr4.ensure(nptr * sizeof(unsigned int)));
     CLP_CUDA(h, cudaMemsetAsync(h->sp_ptr4.p, 0, nptr * sizeof(unsigned int), h->stream));
     a.cnt = h->sp_ptr4.as<unsigned int>();
-    h->counts_fused = true;
   }
   a.d = d; a.p0 = p0; a.p1 = p1; a.p2 = p2; a.p3 = p3; a.affinityeps = h->prm.affinityeps;
   int rc = (h->storage == CLP_STORE_F64) ? launch_score<double>(h, kind, d, a) : launch_score<float>(h, kind, d, a);
@@ -480,6 +483,10 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   SyncBlock host;
   if ((rc = read_sync(h, &host))) return rc;
   if (host.error == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
+  if (a.cnt) {  // the scoring kernel is known to have completed: its counts describe this matrix
+    h->counts_fused = true;
+    h->counts_m = m; h->counts_rows_pad = h->rows_pad; h->counts_nseg = h->plan.NSEG; h->counts_W = h->plan.W;
+  }
   if ((rc = finalize_matrix(h))) return rc;
   h->has_matrix = true;
   h->has_A = true;
@@ -641,6 +648,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
     S.resize((size_t)clp_find_above(u, h->m, 0.0, S.data()));
     const int k = (int)S.size();
     if (k > 0 && h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "Rounding::DSD on a sharded handle");
+    if (k > 8192) return fail(h, CLP_ERR_UNSUPPORTED, "Rounding::DSD: support(u) larger than 8192 nodes");
     if (k > 0) {
       // ship only the k x k sub-block of M induced by support(u)
       CLP_CUDA(h, h->cscbuf.ensure((size_t)k * sizeof(int32_t) + (size_t)k * k * sizeof(double) + 16));
@@ -654,7 +662,6 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
       std::vector<double> sub((size_t)k * k);
       CLP_CUDA(h, cudaMemcpyAsync(sub.data(), sub_d, sub.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CLP_CUDA(h, cudaStreamSynchronize(h->stream));
-      if (k > 8192) return fail(h, CLP_ERR_UNSUPPORTED, "Rounding::DSD: support(u) larger than 8192 nodes");
       // n_total = m: the reference runs dsd::solve on the full M_ restricted to S (clipper.cpp:299)
       const std::vector<int32_t> sel = clp::densest_subgraph_dense(sub.data(), k, h->m);
       nodes.resize(sel.size());
@@ -819,6 +826,7 @@ int clp_score_pointnormal_dev(clp_handle h, const double* D1, int64_t n1, const 
 // ---- get / set ----------------------------------------------------------------------------
 int clp_set_dense(clp_handle h, const double* M, const double* C, int64_t m) {
   if (!h || !M || !C) return CLP_ERR_INVALID;
+  h->counts_fused = false;
   if (int rc = ensure_matrix(h, m)) return rc;
   h->has_A = false; h->A_host_valid = false;
   if (int rc = reset_sync(h)) return rc;
@@ -856,6 +864,7 @@ int clp_set_dense(clp_handle h, const double* M, const double* C, int64_t m) {
 int clp_set_sparse_upper(clp_handle h, int64_t m, const int64_t* cpM, const int32_t* riM, const double* vM,
                          const int64_t* cpC, const int32_t* riC, const double* vC) {
   if (!h || !cpM || !cpC) return CLP_ERR_INVALID;
+  h->counts_fused = false;
   if (int rc = ensure_matrix(h, m)) return rc;
   h->has_A = false; h->A_host_valid = false;
   if (int rc = reset_sync(h)) return rc;
@@ -967,6 +976,8 @@ int clp_solve(clp_handle h, const double* u0, clp_solution* out, double* u_out, 
   if (u0) {
     std::memcpy(stage, u0, (size_t)h->m * sizeof(double));
   } else {  // utils::randvec (ref utils.cpp:22-29): U[0,1) seeded from std::random_device
+    if (h->world > 1)
+      return fail(h, CLP_ERR_INVALID, "sharded solve needs an explicit u0: every rank must start from the same vector");
     std::random_device rd;
     std::mt19937 gen(rd());
     std::uniform_real_distribution<double> dis(0, 1);
@@ -1030,6 +1041,7 @@ struct ShardBlob {  // opaque to the caller; 256 bytes
   void* comm_ptr;
   long long mpad;
   int rank, world, device, pad;
+  unsigned long long seq;    // exchange sequence number of the exporting rank
 };
 static_assert(sizeof(ShardBlob) <= 256, "blob too large");
 }  // namespace
@@ -1038,9 +1050,12 @@ int clp_shard_config(clp_handle h, int rank, int world) {
   if (!h || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
     return fail(h, CLP_ERR_INVALID, "bad shard configuration (1 <= world <= 8)");
   CLP_CUDA(h, cudaSetDevice(h->device));
-  h->rank = rank; h->world = world; h->has_matrix = false; h->shard_ready = false; h->seq = 0;
+  // h->seq is NOT reset: LL tags must never repeat on cells that may still hold values of earlier solves (after a
+  // timed-out solve the ranks' sequence numbers can differ; clp_shard_import re-synchronises them to the maximum)
+  h->rank = rank; h->world = world; h->has_matrix = false; h->shard_ready = false;
   CLP_CUDA(h, h->comm.ensure(sizeof(CommBlock)));
   CLP_CUDA(h, cudaMemset(h->comm.p, 0, sizeof(CommBlock)));
+  if (h->llbuf.p) CLP_CUDA(h, cudaMemset(h->llbuf.p, 0, h->llbuf.cap));  // tag 0 == "never written"
   return CLP_OK;
 }
 
@@ -1064,7 +1079,7 @@ int clp_shard_export(clp_handle h, void* blob, int64_t blob_bytes, int64_t* writ
   CLP_CUDA(h, cudaIpcGetMemHandle(&b.comm, h->comm.p));
   b.pid = (unsigned long long)getpid();
   b.ll_ptr = h->llbuf.p; b.comm_ptr = h->comm.p; b.mpad = h->mpad;
-  b.rank = h->rank; b.world = h->world; b.device = h->device;
+  b.rank = h->rank; b.world = h->world; b.device = h->device; b.seq = h->seq;
   std::memset(blob, 0, 256);
   std::memcpy(blob, &b, sizeof(b));
   if (written) *written = 256;
@@ -1081,9 +1096,11 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
       cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]);
       h->peer_opened[r] = false;
     }
+  unsigned long long seq_max = h->seq;
   for (int r = 0; r < world; ++r) {
     ShardBlob b;
     std::memcpy(&b, reinterpret_cast<const char*>(blobs) + (size_t)r * blob_bytes_each, sizeof(b));
+    seq_max = std::max(seq_max, b.seq);
     if (b.rank != r || b.world != world) return fail(h, CLP_ERR_COMM, "clp_shard_import: blobs are not in rank order");
     if (b.mpad != h->mpad) return fail(h, CLP_ERR_COMM, "clp_shard_import: ranks disagree on the problem size");
     if (r == h->rank) {
@@ -1110,6 +1127,9 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
       h->peer_opened[r] = true; h->peer_open_ptr[r][0] = pv; h->peer_open_ptr[r][1] = pc;
     }
   }
+  // all ranks continue from the same sequence number, beyond every tag any of them has used (a timed-out solve
+  // leaves them different); skipping ahead keeps stale cells from ever validating
+  h->seq = seq_max + 16;
   h->shard_ready = true;
   return CLP_OK;
 }

@@ -4,9 +4,11 @@ Mirrors the reference's benchmark generator (reference benchmarks/main.cpp:156-1
 benchmarks/bm_utils.cpp:111-143,277-349) but deterministic and without its third-party
 dependencies (nanoflann kd-tree, tinyply):
 
-  * cloud: n points on a closed bumpy surface scaled to the unit cube
-    (the reference loads examples/data/bun10k.ply, 9992 points, and calls scale_to_cube(1);
-     the data file is not redistributed here, so a synthetic surface of the same size is used);
+  * cloud: the reference's own benchmark cloud, examples/data/bun10k.ply (9992 float32 points), scaled like
+    scale_to_cube(1) (main.cpp:156-160): read from the reference tree when it is mounted, else from the
+    lossless fixture tests/golden/bun10k_points.npz (written by tests/golden/make_bunny_fixture.py; the GPU
+    box has no /root/reference); a synthetic bumpy closed surface of the same size only if neither exists
+    or another point count is asked for;
   * view 2: D2 = D1 + eta, eta ~ N(0, sigma^2 I3) rejection-truncated to |eta| <= beta
     (main.cpp:31-32,75-83); no rigid transform (main.cpp:161 applies none);
   * associations: ni = round(m(1-rho)) inliers (p,p) drawn without replacement, then
@@ -17,13 +19,60 @@ dependencies (nanoflann kd-tree, tinyply):
 
 Everything is numpy (host side); arrays are returned in the reference's column-major layout.
 """
+import os
+
 import numpy as np
 
 SEED_BASE = 0xC11BBE2
+REFERENCE_PLY = "/root/reference/examples/data/bun10k.ply"
+BUNNY_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             "bun10k_points.npz")
+_cloud_cache = {}
+
+
+def read_ply_xyz(path):
+    """vertices of a binary little-endian PLY whose vertex element is exactly (float x, float y, float z)"""
+    with open(path, "rb") as f:
+        raw = f.read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    header = raw[:end].decode("ascii", "replace").splitlines()
+    if "format binary_little_endian 1.0" not in header:
+        raise ValueError("unsupported PLY format")
+    n = int([ln.split()[2] for ln in header if ln.startswith("element vertex")][0])
+    props = [ln.split()[1:] for ln in header if ln.startswith("property")]
+    if props != [["float", "x"], ["float", "y"], ["float", "z"]]:
+        raise ValueError("unsupported PLY vertex layout: %r" % (props,))
+    return np.frombuffer(raw, dtype="<f4", count=3 * n, offset=end).reshape(n, 3).copy()
+
+
+def bunny_points():
+    """(9992, 3) float32 vertices of the reference's bun10k.ply and where they came from, or (None, why)"""
+    if os.path.exists(REFERENCE_PLY):
+        return read_ply_xyz(REFERENCE_PLY), "reference examples/data/bun10k.ply"
+    if os.path.exists(BUNNY_FIXTURE):
+        return np.load(BUNNY_FIXTURE)["xyz"], "tests/golden/bun10k_points.npz (fixture of bun10k.ply)"
+    return None, "synthetic surface (bun10k.ply and its fixture are both absent)"
+
+
+def cloud_source(n=9992):
+    return bunny_points()[1] if n == 9992 else "synthetic surface (n != 9992)"
+
+
+def scale_to_cube(pts, side=1.0):
+    """reference benchmarks/bm_utils.cpp scale_to_cube: divide by the largest axis extent"""
+    ext = pts.max(axis=0) - pts.min(axis=0)
+    return pts * (side / ext.max())
 
 
 def make_cloud(n=9992, seed=SEED_BASE):
-    """n points on a star-shaped bumpy closed surface, scaled so the largest axis extent is 1."""
+    """3 x n cloud scaled so that its largest axis extent is 1: the bunny for n = 9992 (see module docstring),
+    else n points on a star-shaped bumpy closed surface."""
+    if n == 9992:
+        if "bunny" not in _cloud_cache:
+            xyz, _ = bunny_points()
+            _cloud_cache["bunny"] = None if xyz is None else np.asfortranarray(scale_to_cube(xyz.astype(np.float64)).T)
+        if _cloud_cache["bunny"] is not None:
+            return _cloud_cache["bunny"].copy(order="F")
     rng = np.random.default_rng(seed)
     v = rng.standard_normal((n, 3))
     v /= np.linalg.norm(v, axis=1, keepdims=True)

@@ -13,6 +13,7 @@
  *   - k2ij / createAllToAll / findIndicesOfkLargest / findIndicesWhereAboveThreshold /
  *     selectFromIndicator           reference src/utils.cpp:33-97, include/clipper/utils.h:61-71
  *   - get/setMatrixData             reference src/clipper.cpp:131-166
+ *   - Rounding::DSD (Goldberg)      reference src/dsd.cpp:17-320
  *
  * Storage follows the reference: M_ and C_ are strictly-upper-triangular column-major
  * sparse matrices (CSC) with no diagonal; the identity on the diagonal is applied
@@ -457,6 +458,133 @@ static double now_s(void) {
 
 /* ---- the solver: reference src/clipper.cpp:172-323, statement for statement ---------- */
 
+/* ------------------------------------------------------------------------------------------
+ * Rounding::DSD -- exact densest edge-weighted subgraph (Goldberg's parametric min-cut).
+ * Restates reference src/dsd.cpp:17-272 (graph construction, Dinic max-flow, bisection) and
+ * dsd::solve src/dsd.cpp:274-320 (complete weighted graph on S, weights A(min(i,j),max(i,j))).
+ * Kept exactly: the edge order (all S x S ordered pairs, then src->v, then v->dest), capacities
+ * m/2 (INTEGER division of the edge count, dsd.cpp:25,33,196), paired forward/backward arcs whose
+ * reverse arc starts saturated (dsd.cpp:40-51), the current-arc DFS that pushes one path at a time
+ * and keeps a lowered bottleneck for the later arcs of the same vertex (dsd.cpp:80-102), the cut =
+ * vertices reachable from src in the residual graph (dsd.cpp:106-117), "cut is {src} alone -> U = g,
+ * else L = g" and the stopping rule n(n-1)(U-L) < 1 with n = ALL nodes of A, not |S| (dsd.cpp:216).
+ * Pinned by tests/test_oracle_golden.py against test/dsd_test.cpp:15,38-43,72-79.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t *fin, *nxt, *to, *dist, *Q, *pro, *pro2;
+  double *cap, *flow;
+} dsd_net;
+
+static void dsd_new_edge(dsd_net *g, int64_t u, int64_t v, double w, int64_t *ne) {
+  g->to[*ne] = v; g->cap[*ne] = w; g->flow[*ne] = 0; g->nxt[*ne] = g->fin[u]; g->fin[u] = (*ne)++;
+  g->to[*ne] = u; g->cap[*ne] = w; g->flow[*ne] = w; g->nxt[*ne] = g->fin[v]; g->fin[v] = (*ne)++;
+}
+
+static int dsd_bfs(dsd_net *g, int64_t nverts, int64_t src, int64_t dest) {
+  for (int64_t i = 0; i < nverts; ++i) g->dist[i] = -1;
+  int64_t st = 0, en = 0;
+  g->dist[src] = 0; g->Q[en++] = src;
+  while (st < en) {
+    const int64_t u = g->Q[st++];
+    for (int64_t e = g->fin[u]; e >= 0; e = g->nxt[e]) {
+      const int64_t v = g->to[e];
+      if (g->flow[e] < g->cap[e] && g->dist[v] == -1) { g->dist[v] = g->dist[u] + 1; g->Q[en++] = v; }
+    }
+  }
+  return g->dist[dest] != -1;
+}
+
+static double dsd_dfs(dsd_net *g, int64_t u, double fl, int64_t src, int64_t dest) {
+  if (u == dest) return fl;
+  for (int64_t *e = &g->pro[u]; *e >= 0; *e = g->nxt[*e]) {
+    const int64_t v = g->to[*e];
+    if (g->flow[*e] < g->cap[*e] && g->dist[v] == g->dist[u] + 1) {
+      if (u == src || (g->cap[*e] - g->flow[*e]) <= fl) fl = g->cap[*e] - g->flow[*e];
+      const double df = dsd_dfs(g, v, fl, src, dest);
+      if (df > 0) { g->flow[*e] += df; g->flow[*e ^ 1] -= df; return df; }
+    }
+  }
+  return 0;
+}
+
+static void dsd_find_cut(dsd_net *g, int64_t u, int64_t *cut) {
+  cut[u] = 1;
+  for (int64_t *e = &g->pro2[u]; *e >= 0; *e = g->nxt[*e]) {
+    const int64_t v = g->to[*e];
+    if (g->flow[*e] < g->cap[*e] && cut[v] == 0) dsd_find_cut(g, v, cut);
+  }
+}
+
+/* A = strictly-upper CSC of the affinity matrix (n nodes), S = nS node indices (nS == 0: all nodes).
+ * out receives the selected nodes in ascending order; returns their number. */
+int32_t orc_dsd(const orc_csc *A, const int32_t *S_in, int32_t nS_in, int32_t *out) {
+  const int64_t n = A->m;
+  int64_t nS = nS_in > 0 ? nS_in : n;
+  int32_t *S = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nS > 0 ? nS : 1));
+  for (int64_t q = 0; q < nS; ++q) S[q] = nS_in > 0 ? S_in[q] : (int32_t)q;
+  const int64_t m = nS * nS - nS;            /* dsd.cpp:285 */
+  const int64_t nverts = n + 2, nedges = m + 2 * n;
+  double (*ed)[3] = (double (*)[3])malloc(sizeof(double) * 3 * (size_t)(nedges > 0 ? nedges : 1));
+  double *degree = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+  int64_t k = 0;
+  for (int64_t a = 0; a < nS; ++a)            /* dsd.cpp:293-305 */
+    for (int64_t b = 0; b < nS; ++b) {
+      const int64_t i = S[a], j = S[b];
+      if (i == j) continue;
+      const int64_t r = i < j ? i : j, c = i < j ? j : i;
+      double w = 0.0;                          /* A.coeff(r, c): binary search in column c */
+      int64_t lo = A->colptr[c], hi = A->colptr[c + 1];
+      while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (A->rowidx[mid] < r) lo = mid + 1; else hi = mid; }
+      if (lo < A->colptr[c + 1] && A->rowidx[lo] == r) w = A->val[lo];
+      ed[k][0] = (double)(i + 1); ed[k][1] = (double)(j + 1); ed[k][2] = w;   /* dsd.cpp:186-193 */
+      degree[i] += w;
+      ++k;
+    }
+  double L = 0, U = (double)(m / 2);          /* dsd.cpp:195-196, integer division */
+  dsd_net g;
+  g.Q = (int64_t *)malloc(sizeof(int64_t) * (size_t)nverts);
+  g.fin = (int64_t *)malloc(sizeof(int64_t) * (size_t)nverts);
+  g.pro = (int64_t *)malloc(sizeof(int64_t) * (size_t)nverts);
+  g.pro2 = (int64_t *)malloc(sizeof(int64_t) * (size_t)nverts);
+  g.dist = (int64_t *)malloc(sizeof(int64_t) * (size_t)nverts);
+  g.flow = (double *)malloc(sizeof(double) * 2 * (size_t)nedges);
+  g.cap = (double *)malloc(sizeof(double) * 2 * (size_t)nedges);
+  g.nxt = (int64_t *)malloc(sizeof(int64_t) * 2 * (size_t)nedges);
+  g.to = (int64_t *)malloc(sizeof(int64_t) * 2 * (size_t)nedges);
+  int64_t *cut = (int64_t *)malloc(sizeof(int64_t) * (size_t)nverts);
+  int64_t *final_cut = (int64_t *)calloc((size_t)nverts, sizeof(int64_t));
+  const int64_t src = 0, dest = nverts - 1;
+  while ((double)(n * (n - 1)) * (U - L) >= 1) {   /* dsd.cpp:216 */
+    const double gg = (U + L) / 2;
+    for (int64_t i = m; i < m + n; ++i) { ed[i][0] = (double)src; ed[i][1] = (double)(i - m + 1); ed[i][2] = (double)(m / 2); }
+    for (int64_t i = n + m; i < m + 2 * n; ++i) {
+      ed[i][0] = (double)(i - m - n + 1); ed[i][1] = (double)dest;
+      ed[i][2] = (double)(m / 2) + 2 * gg - degree[i - m - n];
+    }
+    for (int64_t i = 0; i < nverts; ++i) { g.fin[i] = -1; cut[i] = 0; }
+    int64_t ne = 0;
+    for (int64_t i = 0; i < nedges; ++i) dsd_new_edge(&g, (int64_t)ed[i][0], (int64_t)ed[i][1], ed[i][2], &ne);
+    for (int64_t i = 0; i < nverts; ++i) g.pro2[i] = g.fin[i];  /* defined even if the first BFS fails */
+    while (dsd_bfs(&g, nverts, src, dest)) {
+      for (int64_t i = 0; i < nverts; ++i) { g.pro[i] = g.fin[i]; g.pro2[i] = g.fin[i]; }
+      for (;;) { const double df = dsd_dfs(&g, src, 0, src, dest); if (!(df != 0)) break; }
+    }
+    /* NB (dsd.cpp:170): find_cut walks the arc pointers left by the LAST bfs round's copy */
+    dsd_find_cut(&g, src, cut);
+    int64_t in_cut = 0;
+    for (int64_t i = 0; i < nverts; ++i) in_cut += cut[i];
+    if (in_cut == 1) U = gg;
+    else { L = gg; memcpy(final_cut, cut, sizeof(int64_t) * (size_t)nverts); }
+  }
+  final_cut[0] = 0; final_cut[nverts - 1] = 0;
+  int32_t num = 0;
+  for (int64_t i = 1; i < nverts - 1; ++i)
+    if (final_cut[i] != 0) out[num++] = (int32_t)(i - 1);
+  free(S); free(ed); free(degree); free(g.Q); free(g.fin); free(g.pro); free(g.pro2); free(g.dist);
+  free(g.flow); free(g.cap); free(g.nxt); free(g.to); free(cut); free(final_cut);
+  return num;
+}
+
 /* trace (optional, may be NULL): per OUTER iteration i, trace[3*i+0]=F after the inner loop,
  * trace[3*i+1]=d used in that iteration, trace[3*i+2]=number of inner steps; at most trace_cap rows. */
 int orc_solve(const orc_problem *p, const double *u0, const orc_params *P, orc_solution *S,
@@ -584,9 +712,11 @@ int orc_solve(const orc_problem *p, const double *u0, const orc_params *P, orc_s
     const int omega = (int)round(F);
     n_nodes = orc_find_k_largest(u, n, omega, nodes_out);
   } else {
-    /* Rounding::DSD hands support(u) to the host max-flow solver (dsd.cpp:274-320),
-     * which is outside the hot path; the oracle returns the support and flags it. */
-    n_nodes = -orc_find_above(u, n, 0.0, nodes_out);
+    /* Rounding::DSD (clipper.cpp:294-300): densest subgraph of M_ restricted to support(u) */
+    int32_t *supp = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    const int32_t nsupp = orc_find_above(u, n, 0.0, supp);
+    n_nodes = nsupp > 0 ? orc_dsd(M, supp, nsupp, nodes_out) : 0;
+    free(supp);
   }
 
   S->t = now_s() - t1;
@@ -612,4 +742,30 @@ int orc_gradf(const orc_problem *p, const double *v, double d, double *y, double
   if (F) *F = vdot(v, y, n);
   free(Mu); free(Cu);
   return 0;
+}
+
+/* dsd::solve(const Eigen::MatrixXd& A, S) (dsd.cpp:322-325): sparseView of the dense matrix, then the above.
+ * Only the strict upper triangle is ever read (dsd.cpp:300-302), so that is what is converted. */
+int32_t orc_dsd_dense(const double *A, int64_t n, const int32_t *S, int32_t nS, int32_t *out) {
+  orc_csc U;
+  U.m = n;
+  U.colptr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+  int64_t nnz = 0;
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < j; ++i)
+      if (A[(size_t)j * (size_t)n + (size_t)i] != 0.0) ++nnz;
+  U.rowidx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+  U.val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+  int64_t k = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    U.colptr[j] = k;
+    for (int64_t i = 0; i < j; ++i) {
+      const double v = A[(size_t)j * (size_t)n + (size_t)i];
+      if (v != 0.0) { U.rowidx[k] = (int32_t)i; U.val[k] = v; ++k; }
+    }
+  }
+  U.colptr[n] = k;
+  const int32_t r = orc_dsd(&U, S, nS, out);
+  free(U.colptr); free(U.rowidx); free(U.val);
+  return r;
 }

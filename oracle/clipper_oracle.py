@@ -87,6 +87,8 @@ def lib():
         L.orc_get_associations.argtypes = [vp, ip]
         L.orc_matvec.argtypes = [vp, C.c_int, dp, dp]
         L.orc_gradf.argtypes = [vp, dp, C.c_double, dp, dp]
+        L.orc_dsd_dense.restype = C.c_int32
+        L.orc_dsd_dense.argtypes = [dp, C.c_int64, ip, C.c_int32, ip]
         L.orc_solve.argtypes = [vp, dp, C.POINTER(Params), C.POINTER(_Solution), dp, ip, dp, C.c_int64]
         _lib = L
     return _lib
@@ -146,6 +148,17 @@ def euclidean(ai, aj, bi, bj, sigma=0.01, epsilon=0.06, mindist=0.0):
 def pointnormal(ai, aj, bi, bj, sigp=0.5, epsp=0.5, sign=0.10, epsn=0.35):
     v = [np.ascontiguousarray(x, dtype=np.float64) for x in (ai, aj, bi, bj)]
     return lib().orc_pointnormal(_d(v[0]), _d(v[1]), _d(v[2]), _d(v[3]), sigp, epsp, sign, epsn)
+
+
+def dsd_solve(A, S=()):
+    """reference dsd::solve(const Eigen::MatrixXd&, S) (src/dsd.cpp:322-325): A dense symmetric (the strict upper
+    triangle is what is read), S the node subset (empty: all nodes).  Returns the selected nodes, ascending."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    n = A.shape[0]
+    S = np.ascontiguousarray(np.asarray(S, dtype=np.int32))
+    out = np.zeros(max(n, 1), np.int32)
+    k = lib().orc_dsd_dense(_d(A), n, _i(S) if S.size else None, int(S.size), _i(out))
+    return out[:k].tolist()
 
 
 class Solution:
@@ -248,10 +261,7 @@ class Oracle:
         out.t, out.ifinal, out.score, out.d_final = s.t, s.ifinal, s.score, s.d_final
         out.n_evals, out.n_spmv, out.n_inner = s.n_evals, s.n_spmv, s.n_inner
         out.u0, out.u = u0.copy(), u
-        if s.n_nodes >= 0:
-            out.nodes = nodes[: s.n_nodes].copy()
-        else:  # Rounding::DSD: oracle stops at support(u)
-            out.dsd_support = nodes[: -s.n_nodes].copy(); out.nodes = out.dsd_support
+        out.nodes = nodes[: s.n_nodes].copy()
         out.trace = tr[: min(trace_cap, s.ifinal + 1)] if trace_cap else None
         self.soln = out
         return out

@@ -123,7 +123,7 @@ def _golden_cases():
     import glob
     import os
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(here, "*.npz")))
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(here, "*.npz")) if not os.path.basename(p).startswith("bun10k"))
 
 
 @pytest.mark.parametrize("name", _golden_cases())
@@ -148,3 +148,40 @@ def test_oracle_reproduces_golden_files(name):
     s = o.solve(g["u0"])
     assert s.nodes.tolist() == g["nodes"].tolist() and s.score == float(g["score"]) and np.array_equal(s.u, g["u"])
     assert (s.ifinal, s.n_evals, s.n_inner) == (int(g["ifinal"]), int(g["n_evals"]), int(g["n_inner"]))
+
+
+def test_dsd_goldberg_known_answers():
+    # reference test/dsd_test.cpp:15,38-43 (whole graph) and :49,72-79 (search restricted to S)
+    M, _ = fx.m20()
+    assert orc.dsd_solve(M) == fx.DSD_NODES_20
+    assert orc.dsd_solve(M, [0, 1, 3, 5, 7, 12, 14, 15, 19]) == fx.DSD_NODES_20
+    # a 2-node subset: the densest subgraph of an edge is the edge
+    assert orc.dsd_solve(M, [5, 12]) == [5, 12]
+
+
+def test_dsd_rounding_in_solve():
+    # Rounding::DSD (clipper.cpp:294-300) = dsd::solve(M_, support(u)): the nodes are a subset of support(u) and,
+    # on a seeded synthetic problem, exactly the densest subgraph of the support's sub-matrix
+    from clipper_b200 import datagen
+    prob = datagen.euclidean_problem(300, 0.85, 99)
+    o = orc.Oracle(orc.default_params(rounding=orc.DSD))
+    o.score_euclidean(prob["D1"], prob["D2"], prob["A"], sigma=0.015, epsilon=0.05)
+    s = o.solve(prob["u0"])
+    supp = orc.find_above(s.u, 0.0)
+    assert set(s.nodes.tolist()) <= set(supp.tolist()) and len(s.nodes) >= 2
+    assert s.nodes.tolist() == orc.dsd_solve(o.get_affinity_matrix(), supp)
+    # the product's own host DSD (dense Dinic on the support sub-block, clp_host_utils.cpp) agrees with the restatement
+    import clipper_b200 as clp
+    assert clp.dsd.solve(o.get_affinity_matrix(), supp) == s.nodes.tolist()
+
+
+def test_bunny_fixture_matches_ply():
+    # the fixture that travels to the GPU box holds exactly the vertex payload of the reference's bun10k.ply
+    import os
+    from clipper_b200 import datagen
+    z = np.load(datagen.BUNNY_FIXTURE)["xyz"]
+    assert z.shape == (9992, 3) and z.dtype == np.float32
+    if os.path.exists(datagen.REFERENCE_PLY):
+        assert np.array_equal(datagen.read_ply_xyz(datagen.REFERENCE_PLY), z)
+    c = datagen.make_cloud()
+    assert c.shape == (3, 9992) and abs((c.max(axis=1) - c.min(axis=1)).max() - 1.0) < 1e-12
