@@ -282,7 +282,7 @@ def run_ours(args):
     # strict upper triangle only (2 m^2) when every element is applied two-sidedly in-tile (mode 2)
     pass_bytes = (esz * m * m) if mode != 2 else (esz * m * (m - 1) // 2)
     nnz_kept = None
-    if mode == 3:  # compact copy: 6 B per kept entry + item descriptors (clp_sparse_info)
+    if mode in (3, 6):  # compact copy: 6 B per kept entry + item descriptors (clp_sparse_info)
         nnz_kept, pass_bytes = clip.sparse_info()
     alg_bytes = float(np.mean(n_matvec)) * pass_bytes
     kms = float(np.mean(kernel_ms))
@@ -335,7 +335,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (dense M = %.2f GB vs 126 MB L2)" % (esz * m * m / 1e9),
                    "dense_sweep": {0: "segments, full matrix (4 m^2 B/pass)", 1: "stripes, full matrix (4 m^2 B/pass)",
                                    2: "stripes, upper triangle read once, two-sided in-tile update (2 m^2 B/pass)",
-                                   3: "compact sliced-ELL copy: (fp32 value, 16-bit column offset) per kept entry, 6 B/entry/pass"}[mode],
+                                   3: "compact sliced-ELL copy, column segments: (fp32 value, 16-bit column offset) per kept entry, 6 B/entry/pass",
+                                   6: "compact sliced-ELL copy, whole rows, trial vector resident in shared memory: (fp32 value, 16-bit column index) per kept entry, 6 B/entry/pass"}[mode],
                    "kept_entries": nnz_kept, "dense_equivalent_gbs": float(np.mean(n_matvec)) * esz * m * m / (kms * 1e-3) / 1e9,
                    "algorithmic_bytes_per_pass": pass_bytes,
                    "evals_per_solve": float(np.mean(evals)), "matvec_per_solve": float(np.mean(n_matvec)),
@@ -349,11 +350,12 @@ def run_ours(args):
         # kernels of this repository launched per step: gather_endpoints + score_tile + solver, plus the kernels that
         # build the compact copy in mode 3 (sort, item lengths, 2 x scan, fill, partition; + the counting pass when
         # the scoring kernel does not produce the counts itself) -- see profiles/r01g_launches_bench_c2.csv
-        "gpu_launches": ((9 if FUSED_COUNT else 10) if mode == 3 else 3) * args.steps,
+        "gpu_launches": ((9 if FUSED_COUNT else 10) if mode in (3, 6) else 3) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": "solver_kernel<float,%d> (persistent; %d passes over the matrix per launch)"
-                               % (mode, int(round(np.mean(n_matvec)))), "peak_source": peak_src},
+                     "kernel": "%s (persistent; %d passes over the matrix per launch)"
+                               % ("solver_resident_kernel<float>" if mode == 6 else "solver_kernel<float,%d>" % mode,
+                                  int(round(np.mean(n_matvec)))), "peak_source": peak_src},
     }
     if cpu:
         line["cpu_baseline"] = cpu

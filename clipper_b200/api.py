@@ -296,11 +296,12 @@ class CLIPPER:
         _capi.check(self._h, self._lib.clp_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def set_dense_mode(self, mode):
-        """4 (default) auto; 3 compact rows; 2 upper triangle read once, two-sided update; 1 stripes/full; 0 segments"""
+        """4 (default) auto; 6 compact rows + resident trial vector (m <= 27648); 3 compact rows, column segments;
+        2 upper triangle read once, two-sided update; 1 stripes/full; 0 segments"""
         _capi.check(self._h, self._lib.clp_set_dense_mode(self._h, int(mode)))
 
     def set_grid_cap(self, n_ctas):
-        """at most n_ctas CTAs in this object's persistent kernels (0 = every SM); see clipper_b200/batch.py"""
+        """at most n_ctas CTAs in this object's persistent kernels (0 = every SM): lets several shards share one GPU"""
         _capi.check(self._h, self._lib.clp_set_grid_cap(self._h, int(n_ctas)))
 
     def dense_mode(self):

@@ -62,8 +62,9 @@ struct clp_handle_s {
   int ctas_cap = 3;          // user cap (clp_set_ctas_per_sm)
   int head_kb = env_int("CLP_HEAD_KB", 0);       // compact sweep: KB per CTA prefetched into L2 during the sync steps
   int head_where = env_int("CLP_HEAD_WHERE", 1);
-  int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? (ring_ctas > 0 ? ring_ctas : ctas_sparse) : ctas_per_sm); }
+  int ctas_for(int mode) const { return std::min(ctas_cap, mode == 3 ? ctas_sparse : ctas_per_sm); }
   int grid_cap = 0;          // > 0: at most this many CTAs in the persistent kernels (clp_set_grid_cap)
+  int spin_seconds = env_int("CLP_SPIN_SECONDS", 4);  // bound of every in-kernel wait of the resident solver
   int grid_for(int ctas) const { const int g = sm_count * ctas; return grid_cap > 0 ? std::min(g, grid_cap) : g; }
 
   // sharding (row block [row0,row0+rows) of the m x m matrix lives here)
@@ -89,8 +90,14 @@ struct clp_handle_s {
   DevBuf A_dev;                 // int32 [2m]
   DevBuf E1, E2, D1dev, D2dev, F12;  // F12: fp32 positions of both endpoints (screening pass of the scoring kernel)
   int score_filter = env_int("CLP_SCORE_FILTER", 1);
-  int ring_depth = env_int("CLP_SPARSE_RING", 0);   // EXPERIMENTAL cp.async ring sweep of the compact copy: stages (0 = off)
-  int ring_ctas = 0;                                // CTAs/SM the ring instance reaches with its dynamic shared memory
+  // resident-vector solver (clp_resident.cuh): the default whenever the whole trial vector fits shared memory
+  int res_enabled = env_int("CLP_RESIDENT", 1);
+  int res_cfg = env_int("CLP_RES_CFG", -1);         // load pipeline of the resident sweep (-1: automatic), see kResCfgs
+  int res_cfg_eff = 0;
+  int res_G = 0;                                    // CTAs of the resident kernels for the current matrix
+  int res_NI = 0;
+  bool compact_resident = false;                    // layout of the current compact copy: full rows + column indices
+  int smem_optin = 0;                               // cudaDevAttrMaxSharedMemoryPerBlockOptin
   int fuse_count = env_int("CLP_FUSE_COUNT", 1);  // scoring kernel counts the kept entries (skips sparse_count_kernel)
   bool counts_fused = false;                        // sp_ptr4 already holds the counts of the current matrix
   long long counts_m = 0; int counts_rows_pad = 0, counts_nseg = 0, counts_W = 0;  // ... which was this one
@@ -105,6 +112,7 @@ struct clp_handle_s {
   DevBuf u0dev;   // [mpad]
   DevBuf ybuf;    // matvec scratch: v | y | Mv | Cv  (4 x mpad)
   DevBuf sync;    // counter (u64) | error (int) | flags (int) | counts (2 x u64)
+  DevBuf res_vecs, res_cand, res_pieces;  // resident solver: R_SLOTS plain vectors | candidate points | piece table
   DevBuf panel;   // staging panels for get/set dense
   DevBuf cscbuf;
   void* pinned = nullptr;
@@ -113,7 +121,8 @@ struct clp_handle_s {
   long long mpad = 0;
   // stripe decomposition (clp_dense2.cuh)
   int dense_mode = 4;     // requested: 0 segments, 1 stripes/full, 2 stripes/upper-triangle two-sided,
-                          //            3 compact rows, 4 auto (compact rows when the graph is sparse enough, else 2 / 0)
+                          //            3 compact rows (segmented), 6 compact rows + resident vector,
+                          //            4 auto (6 if the vector fits shared memory, else 3, when the graph is sparse enough; else 2 / 0)
   int dense_mode_eff = 2; // effective, decided when the matrix is finalised
   // compact-row copy (clp_sparse.cuh)
   DevBuf sp_val, sp_col, sp_ptr4, sp_part, sp_item, sp_rowid, sp_rank;  // sp_ptr4: kept entries per (segment, row)
@@ -255,10 +264,136 @@ int build_plan2(clp_handle h) {
 }
 
 
+// ------------------------------------------------------------------------------------------
+// resident-vector solver (clp_resident.cuh): load-pipeline configurations, selectable with CLP_RES_CFG for A/B runs
+// ------------------------------------------------------------------------------------------
+struct ResCfg { int NT, U, D, ring; const char* name; };
+const ResCfg kResCfgs[] = {
+    {768, 2, 3, 0, "768 threads, registers: 3 rounds x 2 chunks per lane"},
+    {768, 3, 2, 0, "768 threads, registers: 2 rounds x 3 chunks per lane"},
+    {512, 2, 4, 0, "512 threads, registers: 4 rounds x 2 chunks per lane"},
+    {768, 1, 3, 1, "768 threads, cp.async.bulk ring: 3 stages x 1 chunk per lane"},
+    {768, 2, 3, 1, "768 threads, cp.async.bulk ring: 3 stages x 2 chunks per lane"},
+    {512, 2, 4, 1, "512 threads, cp.async.bulk ring: 4 stages x 2 chunks per lane"},
+    {512, 2, 6, 1, "512 threads, cp.async.bulk ring: 6 stages x 2 chunks per lane"},
+    {512, 2, 2, 0, "512 threads, registers: 2 rounds x 2 chunks per lane (fp64 storage)"},
+};
+constexpr int kResCfgF64 = 7;
+constexpr int kNumResCfgs = (int)(sizeof(kResCfgs) / sizeof(kResCfgs[0]));
+
+// calls f.template operator()<NT, U, D, RING>() for configuration c
+template <typename F>
+auto res_dispatch(int c, F&& f) {
+  switch (c) {
+    case 1: return f.template operator()<768, 3, 2, false>();
+    case 2: return f.template operator()<512, 2, 4, false>();
+    case 3: return f.template operator()<768, 1, 3, true>();
+    case 4: return f.template operator()<768, 2, 3, true>();
+    case 5: return f.template operator()<512, 2, 4, true>();
+    case 6: return f.template operator()<512, 2, 6, true>();
+    case 7: return f.template operator()<512, 2, 2, false>();
+    default: return f.template operator()<768, 2, 3, false>();
+  }
+}
+
+unsigned int res_smem_bytes(clp_handle h, int c) {
+  const ResCfg& k = kResCfgs[c];
+  return res_smem_plan((int)h->m, k.NT / 32, k.ring ? k.D : 0, k.U, (int)h->esize()).total;
+}
+
+// can the resident solver take a problem of this size on this handle?
+bool resident_possible(clp_handle h, long long m) {
+  if (!h->res_enabled || m > kResMaxM || m > 65535) return false;
+  if (!(h->dense_mode == 4 || h->dense_mode == 6)) return false;
+  return (long long)res_smem_plan((int)m, kResThreads / 32, 0, 2, (int)h->esize()).total <= (long long)h->smem_optin;
+}
+
+// the configuration used for the current matrix: the requested one if its shared memory fits, else the register pipeline
+int res_pick_cfg(clp_handle h) {
+  if (h->storage == CLP_STORE_F64) return kResCfgF64;  // 8-byte values: one light register pipeline
+  int c = h->res_cfg;
+  if (c < 0 || c >= kNumResCfgs || c == kResCfgF64) c = 0;
+  if ((long long)res_smem_bytes(h, c) > (long long)h->smem_optin) c = 0;
+  return c;
+}
+
+template <typename T>
+cudaError_t res_set_attrs(clp_handle h, int c, bool sharded) {
+  const int bytes = (int)res_smem_bytes(h, c);
+  return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
+    if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
+    else {
+      cudaError_t e = cudaFuncSetAttribute(matvec_resident_kernel<T, NT, U, D, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) return e;
+      if (sharded) return cudaFuncSetAttribute(solver_resident_kernel<T, NT, U, D, RING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      return cudaFuncSetAttribute(solver_resident_kernel<T, NT, U, D, RING, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    }
+  });
+}
+
+ResArgs res_args(clp_handle h) {
+  ResArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.sp = h->sp;
+  a.m = (int)h->m; a.row0 = h->row0; a.rows = h->rows; a.rows_pad = h->rows_pad; a.NI = h->res_NI; a.G = h->res_G;
+  const clp_params& P = h->prm;
+  a.prm.tol_u = P.tol_u; a.prm.tol_F = P.tol_F; a.prm.beta = P.beta; a.prm.eps = P.eps;
+  a.prm.maxiniters = P.maxiniters; a.prm.maxoliters = P.maxoliters; a.prm.maxlsiters = P.maxlsiters;
+  a.prm.rescale_u0 = P.rescale_u0 ? 1 : 0;
+  a.u0 = h->u0dev.as<double>();
+  a.vecs = h->res_vecs.as<double>();
+  a.cand = h->res_cand.as<double>();
+  a.ll = h->llbuf.as<uint4>();
+  a.mpad = h->mpad;
+  a.pieces = h->res_pieces.as<double>();
+  a.red = h->small.as<double>() + kMaxSeg;
+  a.sb = h->sync.as<SyncBlock>();
+  a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
+  a.out = reinterpret_cast<SolverOut*>(h->result.p);
+  a.rank = h->rank; a.world = h->world; a.seq0 = h->seq;
+  a.comm = h->comm.as<CommBlock>();
+  for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
+  a.spin_limit = (long long)h->spin_seconds * 1900000000LL;
+  a.ring_stages = kResCfgs[h->res_cfg_eff].ring ? kResCfgs[h->res_cfg_eff].D : 0;
+  return a;
+}
+
+template <typename T>
+cudaError_t launch_resident_solver(clp_handle h, ResArgs& a) {
+  const int c = h->res_cfg_eff;
+  const size_t bytes = res_smem_bytes(h, c);
+  void* args[] = {&a};
+  return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
+    if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
+    else {
+      const void* fn = (h->world > 1) ? (const void*)solver_resident_kernel<T, NT, U, D, RING, true>
+                                      : (const void*)solver_resident_kernel<T, NT, U, D, RING, false>;
+      return cudaLaunchCooperativeKernel(fn, dim3(a.G), dim3(NT), args, bytes, h->stream);
+    }
+  });
+}
+
+template <typename T>
+cudaError_t launch_resident_matvec(clp_handle h, const double* v, double d, double* y, double* Mv, double* Cv) {
+  const int c = h->res_cfg_eff;
+  const size_t bytes = res_smem_bytes(h, c);
+  ResArgs a = res_args(h);
+  return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
+    if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
+    else {
+      matvec_resident_kernel<T, NT, U, D, RING><<<a.G, NT, bytes, h->stream>>>(a, v, d, y, Mv, Cv);
+      return cudaGetLastError();
+    }
+  });
+}
+
 // Called once the dense store holds the new matrix: pick the sweep (dense mode) and build what it needs.
 template <typename T>
-int build_sparse(clp_handle h, bool force) {
-  const Plan& p = h->plan;
+int build_sparse(clp_handle h, bool force, bool resident) {
+  // layout of the compact copy: the column segments of the Plan (segmented sweep, byte offsets), or one segment =
+  // the whole row (resident sweep, column indices; padding entries point at column m of the staged vector)
+  Plan p = h->plan;
+  if (resident) { p.NSEG = 1; p.W = (int)h->ld; }
   const int nseg = p.NSEG;
   const long long nptr = (long long)nseg * (h->rows_pad + 1);
   // counts produced by the scoring kernel (scored matrices are "plain"): only trusted for the very matrix and
@@ -283,8 +418,10 @@ int build_sparse(clp_handle h, bool force) {
   CLP_CUDA(h, h->sp_rowid.ensure((size_t)nseg * h->rows_pad * sizeof(unsigned int)));
   CLP_CUDA(h, h->sp_rank.ensure((size_t)nseg * h->rows_pad * sizeof(unsigned int)));
   CLP_CUDA(h, h->sp_item.ensure((size_t)nitem * sizeof(unsigned int)));
-  sell_sort_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->rows_pad, h->sp_rowid.as<unsigned int>(),
-                                                 h->sp_rank.as<unsigned int>(), fused ? &sb->counts[0] : nullptr);
+  const int nb = p.W / 4 + 2;  // possible slice lengths in chunks
+  sell_sort_kernel<<<nseg, 1024, (size_t)(nb + 1) * sizeof(unsigned int), h->stream>>>(
+      h->sp_ptr4.as<unsigned int>(), h->rows_pad, nb, h->sp_rowid.as<unsigned int>(), h->sp_rank.as<unsigned int>(),
+      fused ? &sb->counts[0] : nullptr);
   CLP_CUDA(h, cudaGetLastError());
   sell_itemlen_kernel<<<(unsigned)((nitem + 255) / 256), 256, 0, h->stream>>>(h->sp_ptr4.as<unsigned int>(), h->sp_rowid.as<unsigned int>(),
                                                                               h->rows_pad, nseg, h->sp_item.as<unsigned int>());
@@ -310,11 +447,11 @@ int build_sparse(clp_handle h, bool force) {
   if (!force && !(sparse_bytes < 0.8 * dense_bytes)) return 1;  // keep a dense sweep
   CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(T)));
   CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(unsigned short)));
-  if (h->fill_items && !std::getenv("CLP_PROBE_NO_CONFLICT")) {
+  if (resident || (h->fill_items && !std::getenv("CLP_PROBE_NO_CONFLICT"))) {
     const long long nwarp = (long long)nseg * NI;
     sparse_fill_items_kernel<T><<<(unsigned)((nwarp + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0, h->stream>>>(
         M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg, h->sp_item.as<unsigned int>(), h->sp_rowid.as<unsigned int>(),
-        h->sp_val.as<T>(), h->sp_col.as<unsigned short>());
+        h->sp_val.as<T>(), h->sp_col.as<unsigned short>(), resident ? 0 : 3, resident ? (unsigned int)h->m : kZeroSlot);
   } else {
     sparse_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(M, h->ld, (int)h->m, h->rows, h->rows_pad, p.W, nseg,
                                                          h->sp_item.as<unsigned int>(), h->sp_rank.as<unsigned int>(),
@@ -325,12 +462,26 @@ int build_sparse(clp_handle h, bool force) {
   h->sp.val = h->sp_val.p; h->sp.off16 = h->sp_col.as<unsigned short>();
   h->sp.itemptr = h->sp_item.as<unsigned int>(); h->sp.rowid = h->sp_rowid.as<unsigned int>(); h->sp.rows_pad = h->rows_pad;
   // byte-balanced contiguous item range of every CTA (depends on the grid size: rebuilt with the plan)
-  CLP_CUDA(h, h->sp_part.ensure(2 * ((size_t)p.G + 1) * sizeof(unsigned int)));
-  sparse_partition_kernel<<<(p.G + 1 + 255) / 256, 256, 0, h->stream>>>(h->sp.itemptr, h->rows_pad, nseg, p.G, h->sp_part.as<unsigned int>(),
-                                                                        h->sp_part.as<unsigned int>() + p.G + 1);
+  int G = p.G;
+  if (resident) {  // one fat CTA per SM; small problems use fewer CTAs (>= 2 items each), shards sharing a GPU honour the cap
+    h->res_NI = NI;
+    G = std::max(1, std::min(h->grid_cap > 0 ? std::min(h->grid_cap, h->sm_count) : h->sm_count, NI / 2));
+    h->res_G = G;
+    h->res_cfg_eff = res_pick_cfg(h);
+    CLP_CUDA(h, res_set_attrs<T>(h, h->res_cfg_eff, h->world > 1));
+    const int NW = kResCfgs[h->res_cfg_eff].NT / 32;
+    CLP_CUDA(h, h->res_vecs.ensure((size_t)R_SLOTS * h->mpad * sizeof(double)));
+    CLP_CUDA(h, h->res_cand.ensure((size_t)4 * h->mpad * sizeof(double)));
+    CLP_CUDA(h, h->res_pieces.ensure(((size_t)NI + (size_t)G * NW + 8) * kPieceVals * sizeof(double)));
+    CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * std::max(G, h->plan.G) * kRedVals) * sizeof(double)));
+  }
+  CLP_CUDA(h, h->sp_part.ensure(2 * ((size_t)G + 1) * sizeof(unsigned int)));
+  sparse_partition_kernel<<<(G + 1 + 255) / 256, 256, 0, h->stream>>>(h->sp.itemptr, h->rows_pad, nseg, G, h->sp_part.as<unsigned int>(),
+                                                                      h->sp_part.as<unsigned int>() + G + 1);
   CLP_CUDA(h, cudaGetLastError());
   h->sp.cta_first = h->sp_part.as<unsigned int>();
-  h->sp.cta_chunk = h->sp.cta_first + p.G + 1;
+  h->sp.cta_chunk = h->sp.cta_first + G + 1;
+  h->compact_resident = resident;
   // head of every CTA's range kept warm in L2 across the synchronisation steps: 24 B per chunk (fp32)
   h->sp.head_chunks = (unsigned int)(std::max(0, h->head_kb) * 1024 / (4 * ((int)sizeof(T) + 2)) / 256 * 256);
   h->sp.head_where = h->head_where;
@@ -356,16 +507,18 @@ int set_plan_for(clp_handle h, int mode) {
 
 int finalize_matrix(clp_handle h) {
   int eff = h->dense_mode;
-  if (eff == 3 || eff == 4) {
+  if (eff == 3 || eff == 4 || eff == 6) {
     h->sp.plain = 0;
     if (int rc = set_plan_for(h, 3)) return rc;  // column segmentation (NSEG, W) depends on m only
-    const int rc = (h->storage == CLP_STORE_F64) ? build_sparse<double>(h, eff == 3) : build_sparse<float>(h, eff == 3);
-    if (rc == CLP_OK) eff = 3;
+    const bool resident = (eff != 3) && resident_possible(h, h->m);
+    const bool force = (eff == 3) || (eff == 6);
+    const int rc = (h->storage == CLP_STORE_F64) ? build_sparse<double>(h, force, resident) : build_sparse<float>(h, force, resident);
+    if (rc == CLP_OK) eff = resident ? 6 : 3;
     else if (rc == 1) eff = (h->world > 1) ? 0 : 2;
     else return rc;
   }
   if (eff == 2 && h->world > 1) eff = 1;
-  if (eff != 3) { if (int rc = set_plan_for(h, eff)) return rc; }
+  if (eff != 3 && eff != 6) { if (int rc = set_plan_for(h, eff)) return rc; }
   h->dense_mode_eff = eff;
   if (eff == 1 || eff == 2) { if (int rc = build_plan2(h)) return rc; }
   return CLP_OK;
@@ -387,7 +540,7 @@ int ensure_matrix(clp_handle h, long long m) {
   CLP_CUDA(h, h->vecs.ensure((size_t)V_SLOTS * h->mpad * sizeof(double)));
   {
     void* before = h->llbuf.p;
-    CLP_CUDA(h, h->llbuf.ensure((size_t)L_SLOTS * h->mpad * sizeof(uint4)));
+    CLP_CUDA(h, h->llbuf.ensure((size_t)5 * h->mpad * sizeof(uint4)));  // 3 vectors (segmented solver) / 5 (resident solver)
     if (h->llbuf.p != before) {  // fresh cells carry tag 0 == "never written"
       CLP_CUDA(h, cudaMemset(h->llbuf.p, 0, h->llbuf.cap));
       h->shard_ready = false;
@@ -467,12 +620,14 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   a.A0 = Ad; a.A1 = Ad + m;
   a.M = h->Mbuf.p; a.ld = h->ld; a.m = (int)m; a.row0 = h->row0; a.rows = h->rows; a.rows_pad = h->rows_pad;
   a.F1 = h->F12.as<float4>(); a.F2 = a.F1 + m; a.scale_bits = &sb->scale_bits;
-  a.cnt = nullptr; a.W = h->plan.W;
+  const bool res_layout = resident_possible(h, m);  // the compact copy will use one segment = the whole row
+  const int cnt_nseg = res_layout ? 1 : h->plan.NSEG, cnt_W = res_layout ? (int)h->ld : h->plan.W;
+  a.cnt = nullptr; a.W = cnt_W;
   h->counts_fused = false;
   if (h->score_filter && h->fuse_count && h->storage == CLP_STORE_F32 && (kind == 1 || d == 2 || d == 3) &&
-      (h->dense_mode == 3 || h->dense_mode == 4)) {
+      (h->dense_mode == 3 || h->dense_mode == 4 || h->dense_mode == 6)) {
     // the screened scoring kernel also counts the kept entries per (segment, row): first pass of the compact build
-    const size_t nptr = (size_t)h->plan.NSEG * (h->rows_pad + 1);
+    const size_t nptr = (size_t)cnt_nseg * (h->rows_pad + 1);
     CLP_CUDA(h, h->sp_ptr4.ensure(nptr * sizeof(unsigned int)));
     CLP_CUDA(h, cudaMemsetAsync(h->sp_ptr4.p, 0, nptr * sizeof(unsigned int), h->stream));
     a.cnt = h->sp_ptr4.as<unsigned int>();
@@ -485,7 +640,7 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   if (host.error == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
   if (a.cnt) {  // the scoring kernel is known to have completed: its counts describe this matrix
     h->counts_fused = true;
-    h->counts_m = m; h->counts_rows_pad = h->rows_pad; h->counts_nseg = h->plan.NSEG; h->counts_W = h->plan.W;
+    h->counts_m = m; h->counts_rows_pad = h->rows_pad; h->counts_nseg = cnt_nseg; h->counts_W = cnt_W;
   }
   if ((rc = finalize_matrix(h))) return rc;
   h->has_matrix = true;
@@ -532,6 +687,10 @@ int score_from_device(clp_handle h, int kind, const double* D1d, int d, long lon
 
 template <typename T>
 int launch_matvec(clp_handle h, const StageArgs& st, const double* v, double d, double* y, double* Mv, double* Cv) {
+  if (h->dense_mode_eff == 6) {  // resident layout: stage, sweep and per-row epilogue in one launch
+    CLP_CUDA(h, launch_resident_matvec<T>(h, v, d, y, Mv, Cv));
+    return CLP_OK;
+  }
   const unsigned cb = (unsigned)((h->rows + 255) / 256);
   if (h->dense_mode_eff == 0 || h->dense_mode_eff == 3) {
     const Plan& p = h->plan;
@@ -563,11 +722,6 @@ int matvec_enqueue(clp_handle h, const double* v_dev, double d, double* y_dev, d
 template <typename T>
 cudaError_t launch_solver(clp_handle h, SolverArgs& a) {
   void* args[] = {&a};
-  if constexpr (sizeof(T) == 4) {
-    if (h->dense_mode_eff == 3 && h->ring_ctas > 0)  // experimental ring sweep (clp_sparse.cuh, sparse_phase_ring)
-      return cudaLaunchCooperativeKernel((const void*)solver_kernel<T, 5>, dim3(h->plan.G), dim3(kThreads), args,
-                                         ring_bytes_per_cta(a.ring_depth), h->stream);
-  }
   const void* fn = h->dense_mode_eff == 3 ? (const void*)solver_kernel<T, 3>
                  : h->dense_mode_eff == 2 ? (const void*)solver_kernel<T, 2>
                  : h->dense_mode_eff == 1 ? (const void*)solver_kernel<T, 1> : (const void*)solver_kernel<T, 0>;
@@ -603,7 +757,6 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   a.out = reinterpret_cast<SolverOut*>(h->result.p);
   a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
   a.rank = h->rank; a.world = h->world; a.seq0 = h->seq;
-  a.ring_depth = h->ring_ctas > 0 ? h->ring_depth : 0;
   a.comm = h->comm.as<CommBlock>();
   for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
   if (h->world > 1) {
@@ -613,7 +766,13 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
 
   if (int rc = reset_sync(h)) return rc;
   CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  cudaError_t le = (h->storage == CLP_STORE_F64) ? launch_solver<double>(h, a) : launch_solver<float>(h, a);
+  cudaError_t le;
+  if (h->dense_mode_eff == 6) {
+    ResArgs ra = res_args(h);
+    le = (h->storage == CLP_STORE_F64) ? launch_resident_solver<double>(h, ra) : launch_resident_solver<float>(h, ra);
+  } else {
+    le = (h->storage == CLP_STORE_F64) ? launch_solver<double>(h, a) : launch_solver<float>(h, a);
+  }
   CLP_CUDA(h, le);
   CLP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   const size_t rbytes = 256 + (size_t)h->m * sizeof(double);
@@ -749,17 +908,8 @@ int clp_create(int device, int storage, clp_handle* out) {
   if (e != cudaSuccess || occ < 1 || occ3 < 1) return bail("occupancy query (is the sm_100a image loadable?)", e);
   h->ctas_per_sm = std::min(occ, 2);
   h->ctas_sparse = std::min(occ3, 3);
-  if (h->ring_depth > 0 && storage == CLP_STORE_F32) {  // experimental ring sweep: needs opt-in dynamic shared memory
-    h->ring_depth = std::min(std::max(h->ring_depth, 2), kRingMaxDepth);
-    const size_t rb = ring_bytes_per_cta(h->ring_depth);
-    int occ5 = 0;
-    e = cudaFuncSetAttribute(solver_kernel<float, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ5, solver_kernel<float, 5>, kThreads, rb);
-    if (e != cudaSuccess || occ5 < 1) return bail("ring sweep: dynamic shared memory / occupancy", e);
-    h->ring_ctas = std::min(occ5, 3);
-  } else {
-    h->ring_depth = 0;
-  }
+  if ((e = cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess)
+    return bail("cudaDeviceGetAttribute", e);
 
   *out = h;
   return CLP_OK;
@@ -772,7 +922,7 @@ int clp_destroy(clp_handle h) {
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
   for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->F12, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->sp_part, &h->sp_item, &h->sp_rowid, &h->sp_rank, &h->parts, &h->small,
-                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf})
+                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf, &h->res_vecs, &h->res_cand, &h->res_pieces})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1160,7 +1310,8 @@ int clp_sparse_info(clp_handle h, int64_t* nnz_kept, int64_t* bytes_per_pass) {
   if (!h) return CLP_ERR_INVALID;
   if (nnz_kept) *nnz_kept = (int64_t)h->sp_nnz_real;
   if (bytes_per_pass)
-    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) + (unsigned long long)(h->rows_pad / 4) * h->plan.NSEG * 20);
+    *bytes_per_pass = (int64_t)(h->sp_nnz * (h->esize() + 2) +
+                                (unsigned long long)(h->rows_pad / 4) * (h->compact_resident ? 1 : h->plan.NSEG) * 20);
   return CLP_OK;
 }
 
@@ -1172,7 +1323,7 @@ int clp_get_dense_mode(clp_handle h, int* requested, int* effective) {
 }
 
 int clp_set_dense_mode(clp_handle h, int mode) {
-  if (!h || mode < 0 || mode > 4) return fail(h, CLP_ERR_INVALID, "sweep mode must be 0..4");
+  if (!h || mode < 0 || mode > 6 || mode == 5) return fail(h, CLP_ERR_INVALID, "sweep mode must be 0..4 or 6");
   h->dense_mode = mode;
   if (h->has_matrix) {
     CLP_CUDA(h, cudaSetDevice(h->device));

@@ -919,7 +919,6 @@ struct SolverArgs {
   CommBlock* comm;                  // local
   CommBlock* peer_comm[kMaxPeers];  // every rank's CommBlock (peer_comm[rank] == comm)
   unsigned long long seq0;          // exchange sequence number before this launch
-  int ring_depth;                   // MODE 5 (experimental cp.async ring sweep): stages per lane; last on purpose
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -1037,7 +1036,7 @@ __device__ bool exchange_sums(const SolverArgs& a, const double (&loc)[kRedVals]
 // MODE 0: column-segment decomposition (matvec_phase); 1: stripes, full matrix; 2: stripes, upper triangle
 // read once and applied two-sidedly (single GPU); 3: compact rows (clp_sparse.cuh) in the MODE-0 decomposition
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == 3 || MODE == 5) ? 3 : 2) solver_kernel(SolverArgs a) {
+__global__ void __launch_bounds__(kThreads, MODE == 3 ? 3 : 2) solver_kernel(SolverArgs a) {
   __shared__ __align__(16) double vs[kSegMax + 2];
   __shared__ double red_smem[kWarps * kRedVals + kMaxPeers * kRedVals];
   __shared__ int smem_flag;
@@ -1082,13 +1081,12 @@ __global__ void __launch_bounds__(kThreads, (MODE == 3 || MODE == 5) ? 3 : 2) so
 #define CLP_DENSE_PASS()                                                                    \
   if constexpr (MODE == 0) matvec_phase<T>(mv, p, st, a.partM, a.partC, vs, red_smem);      \
   else if constexpr (MODE == 3) sparse_phase<T, false>(mv, p, st, a.sp, a.partM, a.partC, vs, red_smem); \
-  else if constexpr (MODE == 5) sparse_phase_ring<T, false>(mv, p, st, a.sp, a.partM, a.partC, vs, red_smem, a.ring_depth); \
   else dense2_phase<T, MODE == 2>(mv, a.plan2, st, a.d2, vs);
 #define CLP_GATHER()                                                                        \
-  if constexpr (MODE == 0 || MODE == 3 || MODE == 5) gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv); \
+  if constexpr (MODE == 0 || MODE == 3) gather_partials(a.partM, a.partC, p.NSEG, mv.rows_pad, lr, Mv, Cv); \
   else dense2_gather(mv, a.plan2, a.d2, lr, Mv, Cv);
 #define CLP_SUMV(out)                                                                       \
-  if constexpr (MODE == 0 || MODE == 3 || MODE == 5) { out = 0.0; for (int s_ = 0; s_ < p.NSEG; ++s_) out += __ldcg(a.segsum + s_); } \
+  if constexpr (MODE == 0 || MODE == 3) { out = 0.0; for (int s_ = 0; s_ < p.NSEG; ++s_) out += __ldcg(a.segsum + s_); } \
   else out = block_sum_ordered(a.d2.sumpart, a.plan2.G, red_smem);
 #define CLP_EXCHANGE()                                                                      \
   CLP_LAP(ns_cb);                                                                           \
@@ -1369,3 +1367,4 @@ __global__ void gather_subblock_kernel(const T* M, long long ld, const int* S, i
 }
 
 }  // namespace clp
+#include "clp_resident.cuh"

@@ -1,0 +1,800 @@
+// clp_resident.cuh -- the "resident vector" solver: findDenseClique() (ref clipper.cpp:172-283) with ONE device-wide
+// synchronisation per objective evaluation.
+//
+// Why.  The segmented solver (solver_kernel in clp_kernels.cuh) cuts the columns into segments of <= 4096 so that a
+// CTA's piece of the trial vector fits a small shared-memory buffer; a row's product is then spread over several CTAs,
+// which costs a partial table in HBM, a device-wide barrier between the sweep and the combine step and a second one
+// for the scalar sums: 18 us of fixed cost per evaluation at m = 20 000 (round-1 measurements), 22 us at m = 1000 --
+// the term that capped multi-GPU scaling and made small problems latency-bound.  Here, for every problem whose
+// WHOLE trial vector fits the 227 KB of shared memory of an SM (m <= 27 000 in fp64), one fat CTA per SM keeps the vector
+// resident, every row is owned by exactly one CTA, and the combine step (gradient entry, objective and step-norm
+// partial sums, BOTH candidate next trial points) runs in the tail of the sweep.  Per evaluation:
+//     stage v (L2 -> shared, 8 B per column; exact division by the norm) -> sweep the CTA's rows -> per-row epilogue ->
+//     publish 8 partial sums -> one arrival counter -> every CTA adds the G x 8 table in the same fixed order.
+// No partial table in HBM, no last-arriver serial reduction, no release hop.
+//
+// Layout: the compact sliced-ELL copy of clp_sparse.cuh with ONE segment = the whole row (16-bit column INDEX per
+// entry instead of a byte offset; padding entries point at column m, where the staged vector holds 0.0).  Rows are
+// sorted by length and grouped four at a time (an item, chunk-interleaved).  A CTA owns a contiguous, byte-balanced
+// range of items (sparse_partition_kernel); inside the CTA the warps split the CTA's chunk STREAM evenly, regardless
+// of item boundaries: a warp adds up the part of an item it covers (a "piece") and the per-row epilogue adds the
+// pieces in stream order -- perfect balance inside the SM with one __syncthreads per sweep, and bit-reproducible.
+//
+// Loads: software-pipelined ld.global.nc rounds in registers (D rounds of U chunks per lane in flight), or -- when the
+// shared memory left beside the vector allows it -- a per-warp ring filled with cp.async.bulk (TMA engine, mbarrier
+// completion): bytes in flight then cost no registers.
+//
+// The same kernel body serves three callers: the single-GPU solve (grid = one CTA per SM), one rank of a row-sharded
+// multi-GPU solve (candidate vectors and rank totals cross NVLink as self-validating LL cells) and, with G = 1 and
+// no device-wide synchronisation at all, every problem of a batch of small problems (clp_batch.cuh).
+#pragma once
+
+namespace clp {
+
+constexpr int kResThreads = 768;                  // 24 warps, one CTA per SM
+constexpr int kResWarps = kResThreads / 32;
+constexpr int kResMaxM = 27648;                   // largest m whose fp64 trial vector (+ scratch) fits 227 KB
+constexpr int kPieceVals = 8;                     // a piece: 4 members x (|M| v, C v)
+
+enum ResVec : int { R_U0 = 0, R_U1, R_G0, R_G1, R_MV0, R_MV1, R_CV0, R_CV1, R_SLOTS };
+enum ResStage : int { RS_RAW = 0, RS_DIV = 1, RS_STEP = 2 };
+
+struct ResArgs {
+  SparseView sp;           // full-row compact copy: off16 holds column indices, itemptr [NI + 1], rowid [rows_pad]
+  int m, row0, rows, rows_pad, NI;
+  int G;                   // CTAs working on this problem (== gridDim.x of the solver launch)
+  SolverParams prm;
+  const double* u0;        // [m]
+  double* vecs;            // R_SLOTS plain vectors x mpad (only the entries of the local rows are ever touched)
+  double* cand;            // world == 1: candidate trial points, [2 parities][2: accept, reject][mpad] doubles
+  uint4* ll;               // world  > 1: the same as LL cells + one more vector (final iterate): [5][mpad], replicated
+  long long mpad;
+  double* pieces;          // [(NI + G * warps)][8]
+  double* red;             // [2][G][8] per-CTA partial sums
+  SyncBlock* sb;
+  double* u_final;         // [m]
+  SolverOut* out;
+  int rank, world;
+  uint4* peer_ll[kMaxPeers];
+  CommBlock* comm;
+  CommBlock* peer_comm[kMaxPeers];
+  unsigned long long seq0;
+  long long spin_limit;    // clock64 ticks a wait may last before it raises the time-out flag
+  int ring_stages;         // > 0: cp.async.bulk ring with this many stages per warp (RING instances)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (SASS: SYNCS.*, UBLKCP)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned int parity) {
+  unsigned int ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a bulk copy that never lands raises the error flag instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned int parity, int* error) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) { atomicExch(error, 1); break; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory plan of a resident CTA (dynamic shared memory; the host uses the same function)
+// ---------------------------------------------------------------------------------------------------------------
+struct ResSmem {
+  unsigned int off_red, off_fin, off_wb, off_misc, off_bar, off_ring, total;
+  unsigned int stage_bytes;
+};
+__host__ __device__ inline unsigned int res_round_bytes(int U, int esize) { return (unsigned int)(32 * U * (4 * esize + 8)); }
+__host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages, int U, int esize) {
+  ResSmem s;
+  unsigned int o = (unsigned int)(((m + 1 + 1) & ~1) * 8);        // vs[0..m], vs[m] = 0
+  s.off_red = o; o += (unsigned int)(NW * kRedVals * 8);
+  s.off_fin = o; o += (unsigned int)((2 + kMaxPeers) * kRedVals * 8);
+  s.off_wb = o; o += (unsigned int)((NW + 1) * 4);
+  o = (o + 7u) & ~7u;
+  s.off_misc = o; o += 128;   // per-warp phase bits of the ring's mbarriers (persist from sweep to sweep)
+  s.off_bar = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages * 8 : 0);
+  o = (o + 127u) & ~127u;
+  s.stage_bytes = res_round_bytes(U, esize);
+  s.off_ring = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages : 0) * s.stage_bytes;
+  s.total = o;
+  return s;
+}
+
+// x / y for a divisor shared by many dividends: r = RN(1/y); two residual corrections with FMA.  The last step is
+// Markstein's correction applied to a quotient that is already within an ulp, which rounds like the IEEE division
+// (as the reference's normalize() does) at a third of its instruction count.  Tiny, huge and non-finite operands take
+// the true division.
+__device__ __forceinline__ double div_by_invariant(double x, double y, double r) {
+  const double q0 = x * r;
+  if (!(fabs(q0) > 1e-290 && fabs(q0) < 1e290)) return x / y;  // also 0, NaN, Inf
+  const double e0 = fma(-q0, y, x);
+  const double q1 = fma(e0, r, q0);
+  const double e1 = fma(-q1, y, x);
+  return fma(e1, r, q1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// deterministic block reductions (identical result on every CTA given identical inputs)
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ double res_block_sum(double x, double* red_s, double* fin) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  x = warp_sum(x);
+  __syncthreads();
+  if (lane == 0) red_s[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    double t = (lane < NT / 32) ? red_s[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) fin[0] = t;
+  }
+  __syncthreads();
+  return fin[0];
+}
+
+// per-thread partials loc[8] -> red_row[8] (one CTA's row of the table)
+template <int NT>
+__device__ __forceinline__ void res_publish(const double (&loc)[kRedVals], double* red_row, double* red_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double t[kRedVals];
+#pragma unroll
+  for (int q = 0; q < kRedVals; ++q) t[q] = warp_sum(loc[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) red_s[warp * kRedVals + q] = t[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < kRedVals) {
+    double s = 0.0;
+    for (int w = 0; w < NT / 32; ++w) s += red_s[w * kRedVals + threadIdx.x];
+    red_row[threadIdx.x] = s;
+  }
+}
+
+// every CTA adds the G rows of the table in the same order: thread (q = t & 7, c = t >> 3) walks rows c, c + NT/8, ...;
+// the NT/8 partial groups are then added warp by warp.  Result in fin[0..7] (shared), visible to all threads.
+template <int NT>
+__device__ __forceinline__ void res_reduce_table(const double* table, int G, double* red_s, double* fin) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = threadIdx.x & 7;
+  double s = 0.0;
+  for (int c = threadIdx.x >> 3; c < G; c += NT / 8) s += __ldcg(table + (size_t)c * kRedVals + q);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  __syncthreads();
+  if (lane < kRedVals) red_s[warp * kRedVals + lane] = s;
+  __syncthreads();
+  if (threadIdx.x < kRedVals) {
+    double t = 0.0;
+    for (int w = 0; w < NT / 32; ++w) t += red_s[w * kRedVals + threadIdx.x];
+    fin[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// staging: the whole trial vector into shared memory; returns sum(v) (bit-identical on every CTA)
+//   RS_RAW : v = src                                   (power step on u0, stand-alone mat-vec)
+//   RS_DIV : v = w / |w|                               (u /= u.norm(), clipper.cpp:198 -- no zero guard)
+//   RS_STEP: v = w / |w| if |w|^2 > 0 else w           (unew.normalize(), clipper.cpp:237), w = a candidate point
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT, bool SHARDED>
+__device__ double res_stage(int mode, int m, const double* src, const uint4* cells, unsigned int tag, double z,
+                            double* vs, double* red_s, double* fin, int* errp, long long spin_limit) {
+  const double nrm = sqrt(z);
+  const double rinv = 1.0 / nrm;
+  const bool scale = (mode == RS_DIV) || (mode == RS_STEP && z > 0.0);
+  double part = 0.0;
+  constexpr int kB = 4;  // loads in flight per thread
+  for (int j0 = threadIdx.x; j0 < m; j0 += kB * NT) {
+    double w[kB];
+    if (SHARDED && mode != RS_RAW) {
+      unsigned int lo[kB], t1[kB], hi[kB], t2[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int j = j0 + b * NT;
+        lo[b] = hi[b] = 0u; t1[b] = t2[b] = tag;
+        if (j < m)
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(lo[b]), "=r"(t1[b]), "=r"(hi[b]), "=r"(t2[b]) : "l"(cells + j) : "memory");
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int j = j0 + b * NT;
+        w[b] = 0.0;
+        if (j < m) {
+          if (t1[b] == tag && t2[b] == tag) w[b] = __hiloint2double((int)hi[b], (int)lo[b]);
+          else {  // not there yet: poll (bounded)
+            long long t0 = 0;
+            for (;;) {
+              asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(lo[b]), "=r"(t1[b]), "=r"(hi[b]), "=r"(t2[b]) : "l"(cells + j) : "memory");
+              if (t1[b] == tag && t2[b] == tag) break;
+              if (t0 == 0) t0 = clock64();
+              else if (clock64() - t0 > spin_limit) { atomicExch(errp, 1); break; }
+            }
+            w[b] = __hiloint2double((int)hi[b], (int)lo[b]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int j = j0 + b * NT;
+        w[b] = (j < m) ? __ldcg(src + j) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      const int j = j0 + b * NT;
+      if (j < m) {
+        double v = w[b];
+        if (scale) v = (mode == RS_DIV) ? (w[b] / nrm) : div_by_invariant(w[b], nrm, rinv);
+        vs[j] = v;
+        part += v;
+      }
+    }
+  }
+  if (threadIdx.x == 0) vs[m] = 0.0;  // column of the padding entries
+  return res_block_sum<NT>(part, red_s, fin);  // contains the __syncthreads that publish vs
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the sweep: this CTA's item range of the compact copy against the resident vector -> pieces
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool PLAIN>
+__device__ __forceinline__ void res_apply_chunk(const Entry4<T>& E, const double* vs, double& aM, double& aC) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double v = vs[off_of(E.k, q)];
+    if (PLAIN) {
+      aM = fma((double)E.get(q), v, aM);  // padding: -0.0 * 0.0
+      aC += v;
+    } else {
+      double dM = 0.0, dC = 0.0;
+      apply_elem<false>(E.get(q), v, 0.0, aM, aC, dM, dC);
+    }
+  }
+}
+
+// chunk range [s0, s1) of warp w out of NW over the CTA's stream [c_lo, c_hi): multiples of 4 chunks
+__device__ __forceinline__ unsigned int res_warp_bound(unsigned int c_lo, unsigned int c_hi, int w, int NW) {
+  if (w >= NW) return c_hi;
+  const unsigned long long q = (unsigned long long)((c_hi - c_lo) >> 2);
+  return c_lo + (unsigned int)(q * (unsigned long long)w / (unsigned long long)NW) * 4u;
+}
+
+// smallest index it in [lo, hi] with itemptr[it + 1] > c   (i.e. the non-empty item that holds chunk c)
+__device__ __forceinline__ unsigned int res_item_of(const unsigned int* itemptr, unsigned int lo, unsigned int hi, unsigned int c) {
+  while (lo < hi) {
+    const unsigned int mid = lo + ((hi - lo) >> 1);
+    if (itemptr[mid + 1] > c) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+template <typename T, int NT, int U, int D, bool RING>
+__device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, unsigned char* smem, const ResSmem& plan, int* errp) {
+  constexpr int NW = NT / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SparseView& sp = a.sp;
+  const unsigned int it0 = sp.cta_first[bid], it1 = sp.cta_first[bid + 1];
+  if (it0 >= it1) return;
+  const unsigned int* __restrict__ itemptr = sp.itemptr;
+  const unsigned int c_lo = itemptr[it0], c_hi = itemptr[it1];
+  const unsigned int s0 = res_warp_bound(c_lo, c_hi, warp, NW), s1 = res_warp_bound(c_lo, c_hi, warp + 1, NW);
+  if (s0 >= s1) return;
+  const T* __restrict__ val = reinterpret_cast<const T*>(sp.val);
+  const unsigned short* __restrict__ idx = sp.off16;
+  const unsigned int padk = (unsigned int)a.m | ((unsigned int)a.m << 16);  // column m holds 0.0
+  double* pieces = a.pieces + ((size_t)bid * NW + warp) * kPieceVals;  // + item * 8
+
+  // ---- producer cursor (warp-uniform): the piece being loaded
+  unsigned int cit = res_item_of(itemptr, it0, it1 - 1, s0);
+  unsigned int cj = s0;
+  unsigned int ce = min(itemptr[cit + 1], s1);
+  bool pdone = false;
+  double aM[2] = {0.0, 0.0}, aC[2] = {0.0, 0.0};
+
+  auto advance = [&](unsigned int& jbase, unsigned int& n, unsigned int& item, bool& last) {
+    // describes the next round: first chunk, chunks in it, its item, whether it ends its piece; moves the cursor
+    jbase = cj; item = cit;
+    const unsigned int left = ce - cj;
+    n = left < 32u * U ? left : 32u * U;
+    last = (n == left);
+    if (last) {
+      cj = ce;
+      if (cj >= s1) pdone = true;
+      else {
+        do { ++cit; } while (itemptr[cit + 1] <= cj);  // skip empty items
+        ce = min(itemptr[cit + 1], s1);
+      }
+    } else cj += 32u * U;
+  };
+  auto flush = [&](unsigned int item) {
+    double accM = aM[0] + aM[1], accC = aC[0] + aC[1];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      accM += __shfl_xor_sync(0xffffffffu, accM, o);
+      accC += __shfl_xor_sync(0xffffffffu, accC, o);
+    }
+    if (lane < 4) {
+      double* p = pieces + (size_t)item * kPieceVals;
+      p[lane] = accM; p[4 + lane] = accC;
+    }
+    aM[0] = aM[1] = aC[0] = aC[1] = 0.0;
+  };
+  const bool plain = sp.plain != 0;
+
+  if constexpr (!RING) {
+    // D rounds of U chunks per lane in registers; the refill of a round is issued right after it has been applied,
+    // so D - 1 rounds are always in flight behind the one being consumed
+    Entry4<T> E[D][U];
+    unsigned int mitem[D];
+    bool mlast[D], mvalid[D];
+    auto produce = [&](int s) {
+      mvalid[s] = !pdone;
+      if (pdone) return;
+      unsigned int jb, n;
+      advance(jb, n, mitem[s], mlast[s]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned int c = lane + 32u * u;
+        if (c < n) E[s][u].load(val, idx, 4ull * (jb + c));
+        else E[s][u].neutral_at(padk);
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < D; ++s) produce(s);
+    for (;;) {
+      bool done = false;
+#pragma unroll
+      for (int s = 0; s < D; ++s) {
+        if (!mvalid[s]) { done = true; break; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (plain) res_apply_chunk<T, true>(E[s][u], vs, aM[u & 1], aC[u & 1]);
+          else res_apply_chunk<T, false>(E[s][u], vs, aM[u & 1], aC[u & 1]);
+        }
+        if (mlast[s]) flush(mitem[s]);
+        produce(s);
+      }
+      if (done) break;
+    }
+  } else {
+    // per-warp ring of D stages in shared memory, filled by cp.async.bulk (one copy for the values, one for the
+    // column indices of a round), completion on one mbarrier per stage
+    unsigned char* ring = smem + plan.off_ring + (size_t)warp * D * plan.stage_bytes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + plan.off_bar) + warp * D;
+    unsigned int mitem[D], mn[D];
+    bool mlast[D], mvalid[D];
+    unsigned int* parity_slot = reinterpret_cast<unsigned int*>(smem + plan.off_misc) + warp;
+    unsigned int parity = *parity_slot;  // bit s: phase the consumer waits for on stage s (the barriers live across sweeps)
+    auto produce = [&](int s) {
+      mvalid[s] = !pdone;
+      if (pdone) return;
+      unsigned int jb;
+      advance(jb, mn[s], mitem[s], mlast[s]);
+      if (lane == 0) {
+        unsigned char* st = ring + (size_t)s * plan.stage_bytes;
+        const unsigned int bv = mn[s] * 4u * (unsigned int)sizeof(T), bi = mn[s] * 8u;
+        mbar_expect_tx(&bars[s], bv + bi);
+        bulk_g2s(st, val + 4ull * jb, bv, &bars[s]);
+        bulk_g2s(st + 32u * U * 4u * sizeof(T), idx + 4ull * jb, bi, &bars[s]);
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < D; ++s) produce(s);
+    for (;;) {
+      bool done = false;
+#pragma unroll
+      for (int s = 0; s < D; ++s) {
+        if (!mvalid[s]) { done = true; break; }
+        mbar_wait(&bars[s], (parity >> s) & 1u, errp);
+        parity ^= 1u << s;
+        const unsigned char* st = ring + (size_t)s * plan.stage_bytes;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned int c = lane + 32u * u;
+          Entry4<T> e;
+          if (c < mn[s]) e.load_shared(st + (size_t)c * 4 * sizeof(T), st + 32u * U * 4u * sizeof(T) + (size_t)c * 8);
+          else e.neutral_at(padk);
+          if (plain) res_apply_chunk<T, true>(e, vs, aM[u & 1], aC[u & 1]);
+          else res_apply_chunk<T, false>(e, vs, aM[u & 1], aC[u & 1]);
+        }
+        if (mlast[s]) flush(mitem[s]);
+        __syncwarp();  // every lane has read the stage before the next bulk copy may overwrite it
+        produce(s);
+      }
+      if (done) break;
+    }
+    __syncwarp();
+    if (lane == 0) *parity_slot = parity;
+  }
+}
+
+// sum of the pieces of one row (item it of this CTA, member s) in stream order
+template <int NT>
+__device__ __forceinline__ void res_gather_pieces(const ResArgs& a, const int bid, const unsigned int* wb, unsigned int it, int s,
+                                                  double& Mv, double& Cv) {
+  constexpr int NW = NT / 32;
+  const unsigned int b = a.sp.itemptr[it], e = a.sp.itemptr[it + 1];
+  double m_ = 0.0, c_ = 0.0;
+  if (e > b) {
+    int w0 = 0, w1 = 0;  // warps holding the first and the last chunk of the item: largest w with wb[w] <= chunk
+#pragma unroll 1
+    for (int w = 1; w < NW; ++w) { if (wb[w] <= b) w0 = w; if (wb[w] <= e - 1u) w1 = w; }
+    const double* p = a.pieces + ((size_t)bid * NW + w0 + it) * kPieceVals;
+    for (int w = w0; w <= w1; ++w, p += kPieceVals) {
+      if (wb[w + 1] <= wb[w]) continue;  // warp without chunks
+      m_ += __ldcg(p + s); c_ += __ldcg(p + 4 + s);
+    }
+  }
+  Mv = m_; Cv = c_;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-wide exchange of 8 partial sums: one arrival counter, every CTA reduces the table itself
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT, bool SHARDED, bool SOLO>
+__device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc)[kRedVals], double (&vals)[kRedVals], int& red_par,
+                             unsigned long long& round, unsigned long long& seq, double* red_s, double* fin) {
+  int* errp = &a.sb->error;
+  ++round; ++seq;
+  if constexpr (SOLO) {  // one CTA owns the whole problem: a block reduction is the exchange
+    res_publish<NT>(loc, fin + kRedVals, red_s);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kRedVals; ++q) vals[q] = fin[kRedVals + q];
+    __syncthreads();
+    return true;
+  } else {
+    const int G = a.G;
+    double* table = a.red + (size_t)red_par * G * kRedVals;
+    res_publish<NT>(loc, table + (size_t)bid * kRedVals, red_s);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&a.sb->root[0], 1ULL);
+      const unsigned long long target = round * (unsigned long long)G;
+      const long long t0 = clock64();
+      while (ld_acquire_u64(&a.sb->root[0]) < target) {
+        if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    res_reduce_table<NT>(table, G, red_s, fin);
+    if constexpr (SHARDED) {
+      const unsigned int tag = (unsigned int)seq;
+      const int t = threadIdx.x;
+      if (t < a.world * kRedVals) {
+        const int r = t / kRedVals, q = t % kRedVals;
+        if (bid == 0 && r != a.rank) ll_store(&a.peer_comm[r]->xred[red_par][a.rank][q], fin[q], tag);
+        double x = fin[q];
+        if (r != a.rank) {
+          unsigned lo, t1, hi, t2; long long t0 = 0;
+          const uint4* p = &a.comm->xred[red_par][r][q];
+          for (;;) {
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+            if (t1 == tag && t2 == tag) break;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
+          }
+          x = __hiloint2double((int)hi, (int)lo);
+        }
+        fin[(2 + r) * kRedVals + q] = x;
+      }
+      __syncthreads();
+      if (t < kRedVals) {
+        double s = 0.0;
+        for (int r = 0; r < a.world; ++r) s += fin[(2 + r) * kRedVals + t];
+        fin[kRedVals + t] = s;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kRedVals; ++q) vals[q] = fin[kRedVals + q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < kRedVals; ++q) vals[q] = fin[q];
+    }
+    __syncthreads();
+    red_par ^= 1;
+    return *reinterpret_cast<volatile int*>(errp) == 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the solver body (shared by solver_resident_kernel and the batched kernel)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int NT, int U, int D, bool RING, bool SHARDED, bool SOLO>
+__device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
+  constexpr int NW = NT / 32;
+  const int bid = SOLO ? 0 : (int)blockIdx.x;  // CTA index within the problem (batched: one CTA per problem)
+  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T));
+  double* vs = reinterpret_cast<double*>(smem);
+  double* red_s = reinterpret_cast<double*>(smem + plan.off_red);
+  double* fin = reinterpret_cast<double*>(smem + plan.off_fin);
+  unsigned int* wb = reinterpret_cast<unsigned int*>(smem + plan.off_wb);
+  const SolverParams& P = a.prm;
+  int* const errp = &a.sb->error;
+  const int m = a.m;
+  const long long mp = a.mpad;
+
+  // rows of this CTA: items [it0, it1), four member rows each; thread t serves rows t, t + NT, ... of that list
+  const unsigned int it0 = a.sp.cta_first[bid], it1 = a.sp.cta_first[bid + 1];
+  const int nrow = (int)(it1 - it0) * 4;
+  if (threadIdx.x <= NW) {
+    const unsigned int c_lo = a.sp.itemptr[it0], c_hi = a.sp.itemptr[it1];
+    wb[threadIdx.x] = res_warp_bound(c_lo, c_hi, threadIdx.x, NW);
+  }
+  if constexpr (RING) {
+    if (threadIdx.x < NW * D) mbar_init(reinterpret_cast<unsigned long long*>(smem + plan.off_bar) + threadIdx.x, 1);
+    if (threadIdx.x < NW) reinterpret_cast<unsigned int*>(smem + plan.off_misc)[threadIdx.x] = 0u;
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto V = [&](int slot) -> double* { return a.vecs + (size_t)slot * mp; };
+  // candidate trial points: parity par, kind 0 = "accept" (max(v + gradFnew, 0)), 1 = "reject" (max(u + alpha beta gradF, 0))
+  auto cand_store = [&](int par, int kind, int i, double v, unsigned int tag) {
+    const size_t off = (size_t)(par * 2 + kind) * mp + i;
+    if constexpr (SHARDED) {
+      ll_store(a.ll + off, v, tag);
+      for (int r = 0; r < a.world; ++r)
+        if (r != a.rank) ll_store(a.peer_ll[r] + off, v, tag);
+    } else {
+      a.cand[off] = v;
+    }
+  };
+
+  double vals[kRedVals], loc[kRedVals];
+  long long n_evals = 0, n_inner = 0, n_matvec = 0;
+  int cur = 0, cpar = 0, red_par = 0, status = 0, i_outer = 0;
+  double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0;
+  unsigned long long round = 0, seq = a.seq0;
+  unsigned int ctag = 0u;  // tag under which the candidates of parity cpar were written
+  unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, tmark = global_ns();
+#define RES_LAP(acc) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; }
+#define RES_ZERO() _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
+#define RES_FOR_ROWS(lr, itx, sx)                                                                   \
+  for (int t_ = threadIdx.x; t_ < nrow; t_ += NT)                                                   \
+    if (const unsigned int itx = it0 + (unsigned int)(t_ >> 2); true)                               \
+      if (const int sx = t_ & 3; true)                                                              \
+        if (const int lr = (int)a.sp.rowid[4u * itx + sx]; lr < a.rows)
+#define RES_EXCHANGE()                                                                              \
+  RES_LAP(ns_cb);                                                                                   \
+  if (!res_exchange<NT, SHARDED, SOLO>(a, bid, loc, vals, red_par, round, seq, red_s, fin)) { status = 5; goto finish; } \
+  RES_LAP(ns_ex);
+#define RES_SWEEP()                                                                                 \
+  res_sweep<T, NT, U, D, RING>(a, bid, vs, smem, plan, errp);                                            \
+  ++n_matvec;                                                                                       \
+  __syncthreads();                                                                                  \
+  RES_LAP(ns_mv);
+
+  // ---- phase 0: u = M u0 + u0 (or u0), squared norm (clipper.cpp:193-198) ---------------------
+  {
+    if (P.rescale_u0) {
+      res_stage<NT, SHARDED>(RS_RAW, m, a.u0, nullptr, 0u, 1.0, vs, red_s, fin, errp, a.spin_limit);
+      RES_SWEEP();
+    }
+    RES_ZERO();
+    const unsigned int tag = (unsigned int)(seq + 1);
+    RES_FOR_ROWS(lr, itx, sx) {
+      const int i = a.row0 + lr;
+      double t = a.u0[i];
+      if (P.rescale_u0) {
+        double Mv, Cv;
+        res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+        t = __dadd_rn(Mv, t);
+      }
+      cand_store(cpar ^ 1, 0, i, t, tag);
+      loc[0] += t * t;
+    }
+    RES_EXCHANGE();
+    cpar ^= 1; ctag = tag;
+    z = vals[0];
+  }
+  // ---- phase 1: u /= |u|; Mhat u, Chat u; initial d (clipper.cpp:198-209) ----------------------
+  {
+    const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
+                                               SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
+                                               errp, a.spin_limit);
+    RES_SWEEP();
+    cur = 1;
+    sum_cur = sumu;
+    RES_ZERO();
+    RES_FOR_ROWS(lr, itx, sx) {
+      const int i = a.row0 + lr;
+      double Mv, Cv;
+      res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+      const double ui = vs[i];
+      V(R_U0 + cur)[i] = ui; V(R_MV0 + cur)[i] = Mv; V(R_CV0 + cur)[i] = Cv;
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sumu), Cv), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += __dadd_rn(Mv, ui) / cbu; }
+    }
+    RES_EXCHANGE();
+    if (vals[0] > 0.0) d = vals[1] / vals[0];
+  }
+
+  // ---- graduated projected gradient ascent (clipper.cpp:218-281) --------------------------------
+  for (i_outer = 0; i_outer < P.maxoliters; ++i_outer) {
+    // gradF and F of the current u under the current d (clipper.cpp:219-220) + the first trial point max(u + gradF, 0)
+    {
+      RES_ZERO();
+      const unsigned int tag = (unsigned int)(seq + 1);
+      RES_FOR_ROWS(lr, itx, sx) {
+        const int i = a.row0 + lr;
+        const double ui = V(R_U0 + cur)[i];
+        const double g = grad_entry(ui, sum_cur, V(R_MV0 + cur)[i], V(R_CV0 + cur)[i], d);
+        V(R_G0 + cur)[i] = g;
+        loc[0] += ui * g;
+        double w = __dadd_rn(ui, __dmul_rn(1.0, g)); w = (w < 0.0) ? 0.0 : w;
+        loc[1] += w * w;
+        cand_store(cpar ^ 1, 0, i, w, tag);
+      }
+      RES_EXCHANGE();
+      cpar ^= 1; ctag = tag;
+      F = vals[0]; z = vals[1];
+    }
+    int ckind = 0;  // which candidate of parity cpar the next evaluation tries
+    for (int j = 0; j < P.maxiniters; ++j) {
+      double alpha = 1.0;
+      double Fnew = 0.0, deltaF = 0.0, du2 = 0.0, zB = 0.0, sum_trial = sum_cur;
+      const int nxt = cur ^ 1;
+      for (int k = 0; k < P.maxlsiters; ++k) {
+        // trial point into shared memory, sweep of the CTA's rows
+        const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
+        const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
+                                                   vs, red_s, fin, errp, a.spin_limit);
+        RES_SWEEP();
+        ++n_evals;
+        // per-row epilogue: gradFnew, Fnew, |unew - u|^2 and BOTH possible next trial points
+        const double alpha_rej = __dmul_rn(alpha, P.beta);
+        RES_ZERO();
+        const unsigned int tag = (unsigned int)(seq + 1);
+        RES_FOR_ROWS(lr, itx, sx) {
+          const int i = a.row0 + lr;
+          double Mv, Cv;
+          res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+          const double un = vs[i];
+          const double g = grad_entry(un, sumv, Mv, Cv, d);
+          V(R_U0 + nxt)[i] = un; V(R_G0 + nxt)[i] = g; V(R_MV0 + nxt)[i] = Mv; V(R_CV0 + nxt)[i] = Cv;
+          const double uo = V(R_U0 + cur)[i], go = V(R_G0 + cur)[i];
+          loc[0] += un * g;
+          const double du = __dsub_rn(un, uo);
+          loc[1] += du * du;
+          double wa = __dadd_rn(uo, __dmul_rn(alpha_rej, go)); wa = (wa < 0.0) ? 0.0 : wa;
+          loc[2] += wa * wa;
+          double wb_ = __dadd_rn(un, __dmul_rn(1.0, g)); wb_ = (wb_ < 0.0) ? 0.0 : wb_;
+          loc[3] += wb_ * wb_;
+          cand_store(cpar ^ 1, 0, i, wb_, tag);
+          cand_store(cpar ^ 1, 1, i, wa, tag);
+        }
+        RES_EXCHANGE();
+        cpar ^= 1; ctag = tag;
+        // the line-search decision (clipper.cpp:242-251), identical on every CTA / rank
+        Fnew = vals[0]; du2 = vals[1]; zB = vals[3];
+        deltaF = Fnew - F;
+        sum_trial = sumv;
+        if (deltaF < -P.eps) {
+          alpha = alpha_rej;
+          if (k + 1 < P.maxlsiters) { z = vals[2]; ckind = 1; continue; }
+        }
+        break;
+      }
+      // accept (also when the line search ran out, clipper.cpp:256-258)
+      const double deltau = sqrt(du2);
+      F = Fnew; cur = nxt; sum_cur = sum_trial; z = zB; ckind = 0;
+      ++n_inner;
+      if (deltau < P.tol_u || fabs(deltaF) < P.tol_F) break;
+    }
+    // penalty ramp (clipper.cpp:268-280)
+    RES_ZERO();
+    RES_FOR_ROWS(lr, itx, sx) {
+      const int i = a.row0 + lr;
+      const double ui = V(R_U0 + cur)[i];
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), V(R_CV0 + cur)[i]), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(V(R_MV0 + cur)[i], ui) / cbu); }
+    }
+    RES_EXCHANGE();
+    if (vals[0] > 0.0) d += vals[1] / vals[0];
+    else break;
+  }
+
+  // ---- the final iterate ---------------------------------------------------------------------
+  if constexpr (SHARDED) {
+    const unsigned int tag = (unsigned int)(seq + 1);
+    const size_t off = (size_t)4 * mp;
+    RES_FOR_ROWS(lr, itx, sx) {
+      const int i = a.row0 + lr;
+      const double ui = V(R_U0 + cur)[i];
+      ll_store(a.ll + off + i, ui, tag);
+      for (int r = 0; r < a.world; ++r)
+        if (r != a.rank) ll_store(a.peer_ll[r] + off + i, ui, tag);
+    }
+    RES_ZERO();
+    RES_EXCHANGE();  // also the last rendez-vous: no rank overwrites a peer's cells while it is still inside this launch
+    for (int i = bid * NT + threadIdx.x; i < m; i += a.G * NT) a.u_final[i] = ll_load(a.ll + off + i, tag, errp);
+  } else {
+    RES_FOR_ROWS(lr, itx, sx) { const int i = a.row0 + lr; a.u_final[i] = V(R_U0 + cur)[i]; }
+  }
+
+finish:
+  if (bid == 0 && threadIdx.x == 0) {
+    if (*reinterpret_cast<volatile int*>(errp) != 0) status = 5;
+    a.out->F = F; a.out->d = d; a.out->ifinal = i_outer; a.out->cur = cur; a.out->status = status;
+    a.out->n_evals = n_evals; a.out->n_inner = n_inner; a.out->n_matvec = n_matvec; a.out->seq_end = seq;
+    a.out->ns_matvec = ns_mv; a.out->ns_combine = ns_cb; a.out->ns_exchange = ns_ex;
+  }
+#undef RES_LAP
+#undef RES_ZERO
+#undef RES_FOR_ROWS
+#undef RES_EXCHANGE
+#undef RES_SWEEP
+}
+
+template <typename T, int NT, int U, int D, bool RING, bool SHARDED>
+__global__ void __launch_bounds__(NT, 1) solver_resident_kernel(ResArgs a) {
+  extern __shared__ __align__(128) unsigned char clp_res_smem[];
+  res_solve_body<T, NT, U, D, RING, SHARDED, false>(a, clp_res_smem);
+}
+
+// stand-alone mat-vec on the resident layout: stage v, sweep, per-row epilogue -- one launch, no device-wide barrier
+template <typename T, int NT, int U, int D, bool RING>
+__global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const double* v, double dpen, double* y,
+                                                                double* Mv_out, double* Cv_out) {
+  extern __shared__ __align__(128) unsigned char clp_res_smem[];
+  unsigned char* smem = clp_res_smem;
+  constexpr int NW = NT / 32;
+  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T));
+  double* vs = reinterpret_cast<double*>(smem);
+  double* red_s = reinterpret_cast<double*>(smem + plan.off_red);
+  double* fin = reinterpret_cast<double*>(smem + plan.off_fin);
+  unsigned int* wb = reinterpret_cast<unsigned int*>(smem + plan.off_wb);
+  const int bid = (int)blockIdx.x;
+  const unsigned int it0 = a.sp.cta_first[bid], it1 = a.sp.cta_first[bid + 1];
+  if (threadIdx.x <= NW) wb[threadIdx.x] = res_warp_bound(a.sp.itemptr[it0], a.sp.itemptr[it1], threadIdx.x, NW);
+  if constexpr (RING) {
+    if (threadIdx.x < NW * D) mbar_init(reinterpret_cast<unsigned long long*>(smem + plan.off_bar) + threadIdx.x, 1);
+    if (threadIdx.x < NW) reinterpret_cast<unsigned int*>(smem + plan.off_misc)[threadIdx.x] = 0u;
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const double sumv = res_stage<NT, false>(RS_RAW, a.m, v, nullptr, 0u, 1.0, vs, red_s, fin, &a.sb->error, a.spin_limit);
+  res_sweep<T, NT, U, D, RING>(a, bid, vs, smem, plan, &a.sb->error);
+  __syncthreads();
+  const int nrow = (int)(it1 - it0) * 4;
+  for (int t = threadIdx.x; t < nrow; t += NT) {
+    const unsigned int itx = it0 + (unsigned int)(t >> 2);
+    const int sx = t & 3;
+    const int lr = (int)a.sp.rowid[4u * itx + sx];
+    if (lr >= a.rows) continue;
+    double Mv, Cv;
+    res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+    const int i = a.row0 + lr;
+    if (Mv_out) Mv_out[i] = Mv;
+    if (Cv_out) Cv_out[i] = Cv;
+    if (y) y[i] = grad_entry(vs[i], sumv, Mv, Cv, dpen);
+  }
+}
+
+}  // namespace clp

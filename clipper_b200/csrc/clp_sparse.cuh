@@ -92,13 +92,14 @@ __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, i
   }
 }
 
-// pass 2: one block per column segment sorts the rows by slice length, longest first (counting sort over the
-// <= 1025 possible lengths; ties in arrival order, which does not influence any result).
+// pass 2: one block (1024 threads) per column segment sorts the rows by slice length, longest first (counting sort
+// over the nb = W/4 + 2 possible lengths in chunks; ties in arrival order, which does not influence any result).
 //   rowid[seg][pos] = row at sorted position pos, rank[seg][row] = its position
-__global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, unsigned int* rowid, unsigned int* rank,
+// Dynamic shared memory: (nb + 1) counters.
+__global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, int nb, unsigned int* rowid, unsigned int* rank,
                                  unsigned long long* total_entries /* nullable: += kept entries */) {
-  __shared__ unsigned int hist[kSegMax / 4 + 2];
-  const int nb = kSegMax / 4 + 1;
+  extern __shared__ unsigned int hist[];
+  __shared__ unsigned int wsum[32];
   const unsigned int* c = cnt4 + (size_t)blockIdx.x * (rows_pad + 1);
   for (int i = threadIdx.x; i <= nb; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
@@ -110,9 +111,29 @@ __global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, unsigne
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total_entries, mine);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // start of every length class, longest class first
-    unsigned int run = 0;
-    for (int b = nb - 1; b >= 0; --b) { const unsigned int h = hist[b]; hist[b] = run; run += h; }
+  {  // start of every length class, longest class first: exclusive scan of the histogram read backwards
+    const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int r0 = (int)threadIdx.x * per;          // reversed positions [r0, r0 + per): bin = nb - 1 - r
+    unsigned int local = 0;
+    for (int q = 0; q < per; ++q) { const int r = r0 + q; if (r < nb) local += hist[nb - 1 - r]; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      unsigned int v = wsum[lane], t = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+      wsum[lane] = t - v;
+    }
+    __syncthreads();
+    unsigned int run = wsum[w] + (inc - local);
+    for (int q = 0; q < per; ++q) {
+      const int r = r0 + q;
+      if (r < nb) { const unsigned int hcount = hist[nb - 1 - r]; hist[nb - 1 - r] = run; run += hcount; }
+    }
   }
   __syncthreads();
   for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) {
@@ -244,7 +265,9 @@ constexpr int kRing = 256;  // entries per member ring: < 36 left after a flush 
 template <typename T>
 __global__ void __launch_bounds__(kFillWarps * 32)
 sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
-                         const unsigned int* itemptr, const unsigned int* rowid, T* val, unsigned short* off16) {
+                         const unsigned int* itemptr, const unsigned int* rowid, T* val, unsigned short* off16,
+                         int off_shift /* 3: byte offset of v[col] in the staged segment; 0: column index */,
+                         unsigned int pad_off /* offset stored in padding entries: a slot that holds 0.0 */) {
   __shared__ __align__(16) T ringv[kFillWarps][4][kRing];
   __shared__ __align__(8) unsigned short ringo[kFillWarps][4][kRing];
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -269,7 +292,7 @@ sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad
       const unsigned int w = 4u * k + q;
       const bool have = w < nm;
       x[q] = have ? rv[ms][w & (kRing - 1)] : encode<T>(0.0, false);
-      o[q] = have ? ro[ms][w & (kRing - 1)] : (unsigned short)kZeroSlot;
+      o[q] = have ? ro[ms][w & (kRing - 1)] : (unsigned short)pad_off;
     }
     const unsigned long long at = 4ull * (b + 4ull * k + ms);
     Quad<T>::store(val + at, x);
@@ -300,7 +323,7 @@ sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad
       unsigned int w = n[s_] + (pre - cnt);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (keep & (1u << q)) { rv[s_][w & (kRing - 1)] = x[q]; ro[s_][w & (kRing - 1)] = (unsigned short)(8 * (j + q - c0)); ++w; }
+        if (keep & (1u << q)) { rv[s_][w & (kRing - 1)] = x[q]; ro[s_][w & (kRing - 1)] = (unsigned short)((j + q - c0) << off_shift); ++w; }
       n[s_] += total;
     }
     __syncwarp();
@@ -336,6 +359,10 @@ template <> struct Entry4<float> {
   }
   __device__ __forceinline__ float get(int e) const { return e == 0 ? x.x : e == 1 ? x.y : e == 2 ? x.z : x.w; }
   __device__ __forceinline__ void neutral() { x = make_float4(-0.f, -0.f, -0.f, -0.f); k = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16)); }
+  __device__ __forceinline__ void neutral_at(unsigned int kk) { x = make_float4(-0.f, -0.f, -0.f, -0.f); k = make_uint2(kk, kk); }
+  __device__ __forceinline__ void load_shared(const void* pv, const void* pi) {
+    x = *reinterpret_cast<const float4*>(pv); k = *reinterpret_cast<const uint2*>(pi);
+  }
 };
 template <> struct Entry4<double> {
   double2 a, b; uint2 k;
@@ -346,6 +373,10 @@ template <> struct Entry4<double> {
   }
   __device__ __forceinline__ double get(int e) const { return e == 0 ? a.x : e == 1 ? a.y : e == 2 ? b.x : b.y; }
   __device__ __forceinline__ void neutral() { a = make_double2(-0.0, -0.0); b = a; k = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16)); }
+  __device__ __forceinline__ void neutral_at(unsigned int kk) { a = make_double2(-0.0, -0.0); b = a; k = make_uint2(kk, kk); }
+  __device__ __forceinline__ void load_shared(const void* pv, const void* pi) {
+    a = reinterpret_cast<const double2*>(pv)[0]; b = reinterpret_cast<const double2*>(pv)[1]; k = *reinterpret_cast<const uint2*>(pi);
+  }
 };
 __device__ __forceinline__ unsigned int off_of(const uint2& k, int e) {
   return e == 0 ? (k.x & 0xffffu) : e == 1 ? (k.x >> 16) : e == 2 ? (k.y & 0xffffu) : (k.y >> 16);
@@ -525,168 +556,5 @@ __device__ void sparse_phase(const MatView& mv, const Plan& p, const StageArgs& 
   }
 }
 
-
-// ------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL variant of the sweep (solver_kernel<T, 5>, CLP_SPARSE_RING=<depth>; not validated on hardware in
-// round 1): the rounds travel through a lane-private ring in dynamic shared memory filled
-// with cp.async, so the bytes in flight per lane are (depth - 1) rounds and cost no registers.  Every lane copies
-// its own chunks and later reads back only what it copied itself: cp.async.wait_group is the only ordering the
-// data needs.  Per stage a few words of metadata written by the warp tell the consumer which item the round
-// belongs to.  The arithmetic is sell_apply's with kRingUnroll chunks per round.
-constexpr int kRingUnroll = 2;   // chunks per lane and round
-constexpr int kRingMaxDepth = 8;
-__host__ __device__ constexpr size_t ring_bytes_per_cta(int depth) {
-  return (size_t)kWarps * depth * (kRingUnroll * 32 * 24 + 32);  // chunks (16 + 8 B per lane) + 8 words of metadata
-}
-
-__device__ __forceinline__ unsigned char* dynamic_smem() {
-  extern __shared__ __align__(16) unsigned char clp_dyn_smem[];
-  return clp_dyn_smem;
-}
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
-  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n groups still in flight
-  switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-  }
-}
-
-template <typename T, bool PLAIN_ONLY>
-__device__ void sparse_phase_ring(const MatView& mv, const Plan& p, const StageArgs& st, const SparseView& sp,
-                                  double* partM, double* partC, double* vs, double* red_smem, int ring_depth) {
-  static_assert(sizeof(T) == 4, "the ring is laid out for fp32 storage");
-  __shared__ int next_item;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NI = sp.rows_pad >> 2;
-  const int D = min(max(ring_depth, 2), kRingMaxDepth);
-  // this warp's part of the ring: values [D][U][32] x 16 B, offsets [D][U][32] x 8 B, metadata [D][8] words
-  unsigned char* base = dynamic_smem() + (size_t)warp * D * (kRingUnroll * 32 * 24 + 32);
-  T (*rv)[4] = reinterpret_cast<T (*)[4]>(base);                                          // chunk values (fp32 only)
-  uint2* ro = reinterpret_cast<uint2*>(base + (size_t)D * kRingUnroll * 32 * 16);          // chunk offsets
-  unsigned int* meta = reinterpret_cast<unsigned int*>(base + (size_t)D * kRingUnroll * 32 * 24);  // [D][8]
-  const T* val = reinterpret_cast<const T*>(sp.val);
-
-  unsigned int g = sp.cta_first[blockIdx.x];
-  const unsigned int gend = sp.cta_first[blockIdx.x + 1];
-  if (threadIdx.x == 0) vs[kSegMax] = 0.0;
-  for (int seg = (int)(g / (unsigned int)NI); g < gend; ++seg) {
-    const int it0 = (int)(g - (unsigned int)seg * NI);
-    const int it1 = (int)min(gend - (unsigned int)seg * NI, (unsigned int)NI);
-    if (threadIdx.x == 0) next_item = it0 + kWarps;
-    stage_segment<double>(st, p, mv.m, seg, it0 == 0, vs, red_smem);
-    const unsigned int* ipseg = sp.itemptr + (size_t)seg * (NI + 1);
-    const unsigned int* rowseg = sp.rowid + (size_t)seg * sp.rows_pad;
-    auto fetch = [&](int it) -> unsigned int {  // lanes 0,1: chunk range of the item; lanes 2..5: its member rows
-      if (it >= it1) return 0u;
-      if (lane < 2) return ipseg[it + lane];
-      if (lane < 6) return rowseg[4 * it + lane - 2];
-      return 0u;
-    };
-    int it = it0 + warp;
-    if (it < it1) {
-      // ---- producer state (warp-uniform): the item being copied and the descriptor of the one after it
-      unsigned int q0 = fetch(it);
-      int itn = 0;
-      if (lane == 0) itn = atomicAdd(&next_item, 1);
-      itn = __shfl_sync(0xffffffffu, itn, 0);
-      unsigned int q1 = fetch(itn);
-      unsigned int pj = __shfl_sync(0xffffffffu, q0, 0);     // first chunk of the next round to copy
-      unsigned int pe = __shfl_sync(0xffffffffu, q0, 1);     // end of the item being copied
-      unsigned int prow = __shfl_sync(0xffffffffu, q0, 2 + (lane & 3));
-      bool pdone = false;                                     // no item left to copy
-      // copies one round into stage s (or marks the stage "end of stream") and commits the group
-      auto produce = [&](int s) {
-        unsigned int flag = 2u;  // 0: inside an item, 1: last round of its item, 2: end of stream
-        if (!pdone) {
-          const bool last = pj + 32u * kRingUnroll >= pe;
-          flag = last ? 1u : 0u;
-#pragma unroll
-          for (int u = 0; u < kRingUnroll; ++u) {
-            const unsigned int c = pj + lane + 32u * u;
-            T* dv = rv[(s * kRingUnroll + u) * 32 + lane];
-            uint2* dof = ro + (s * kRingUnroll + u) * 32 + lane;
-            if (c < pe) { cp_async_16(dv, val + 4ull * c); cp_async_8(dof, sp.off16 + 4ull * c); }
-            else {
-              dv[0] = dv[1] = dv[2] = dv[3] = encode<T>(0.0, false);
-              *dof = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16));
-            }
-          }
-          if (lane < 4) meta[s * 8 + lane] = prow;
-          if (last) {  // move on to the next item
-            if (itn >= it1) pdone = true;
-            else {
-              pj = __shfl_sync(0xffffffffu, q1, 0); pe = __shfl_sync(0xffffffffu, q1, 1);
-              prow = __shfl_sync(0xffffffffu, q1, 2 + (lane & 3));
-              if (lane == 0) itn = atomicAdd(&next_item, 1);
-              itn = __shfl_sync(0xffffffffu, itn, 0);
-              q1 = fetch(itn);
-            }
-          } else pj += 32u * kRingUnroll;
-        }
-        if (lane == 4) meta[s * 8 + 4] = flag;
-        cp_async_commit();
-      };
-      for (int s = 0; s < D - 1; ++s) produce(s);
-      double aM[2] = {0.0, 0.0}, aC[2] = {0.0, 0.0};
-      int sc = 0, sprod = D - 1;              // stage consumed now / stage refilled now (= consumed in the previous trip)
-      for (;; sc = (sc + 1 == D) ? 0 : sc + 1, sprod = (sprod + 1 == D) ? 0 : sprod + 1) {
-        produce(sprod);
-        cp_async_wait_pending(D - 1);         // the group of round r has landed
-        __syncwarp();                         // metadata of stage sc (written by lanes 0..4) visible to all lanes
-        const unsigned int flag = meta[sc * 8 + 4];
-        if (flag == 2u) break;
-#pragma unroll
-        for (int u = 0; u < kRingUnroll; ++u) {
-          const float4 x = *reinterpret_cast<const float4*>(rv[(sc * kRingUnroll + u) * 32 + lane]);
-          const uint2 k = ro[(sc * kRingUnroll + u) * 32 + lane];
-          const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double v = vs_at(vs, off_of(k, q));
-            if (PLAIN_ONLY || sp.plain) {
-              aM[u & 1] = fma((double)xs[q], v, aM[u & 1]);
-              aC[u & 1] += v;
-            } else {
-              double dummyM = 0.0, dummyC = 0.0;
-              apply_elem<false>(xs[q], v, 0.0, aM[u & 1], aC[u & 1], dummyM, dummyC);
-            }
-          }
-        }
-        if (flag == 1u) {
-          double accM = aM[0] + aM[1], accC = aC[0] + aC[1];
-#pragma unroll
-          for (int o = 4; o < 32; o <<= 1) {
-            accM += __shfl_xor_sync(0xffffffffu, accM, o);
-            accC += __shfl_xor_sync(0xffffffffu, accC, o);
-          }
-          if (lane < 4) {
-            const unsigned int row = meta[sc * 8 + lane];
-            partM[(size_t)seg * mv.rows_pad + row] = accM;
-            partC[(size_t)seg * mv.rows_pad + row] = accC;
-          }
-          aM[0] = aM[1] = aC[0] = aC[1] = 0.0;
-        }
-        __syncwarp();                         // stage sc may be overwritten by the next trip's produce()
-      }
-      cp_async_wait_pending(0);
-    }
-    __syncthreads();  // vs, next_item and the ring are re-used by the next segment pass
-    g = (unsigned int)(seg + 1) * NI;
-  }
-}
 
 }  // namespace clp

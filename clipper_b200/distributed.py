@@ -131,6 +131,11 @@ class ShardedCLIPPER(CLIPPER):
             self._connect()
             self._connected_for = m
 
+    def solve(self, u0=None):
+        """collective solve; a host barrier first, so that the in-kernel peer waits only ever cover kernel skew"""
+        self._dist.barrier(group=self._group)
+        super().solve(u0)
+
     def count_nonzeros(self):
         import torch
         a, b = super().count_nonzeros()
@@ -151,7 +156,12 @@ class ShardGroup:
             c = CLIPPER(make_invariant(), params, device=dev, storage=storage)
             _capi.check(c.handle, L.clp_shard_config(c.handle, r, self.world))
             if same_device:
+                # the shards' persistent kernels must be co-resident on the one GPU: 1 CTA/SM each for the segmented
+                # kernels, and SMs/world fat CTAs each for the resident-vector kernel (it takes a whole SM's shared memory)
+                import torch
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
                 _capi.check(c.handle, L.clp_set_ctas_per_sm(c.handle, 1))
+                _capi.check(c.handle, L.clp_set_grid_cap(c.handle, max(1, sms // self.world)))
             self.shards.append(c)
         self._connected_for = None
 
@@ -335,7 +345,7 @@ def run_bench(args, METRIC, UNIT):
         if float(ok[0]) == 0.0:
             e2e_ms = None
         mode = clip.dense_mode()
-        if mode == 3:
+        if mode in (3, 6):
             kept, pass_bytes = clip.sparse_info()      # this rank's rows
         else:
             r0, nrows = shard_rows(m, rank, world)
@@ -381,7 +391,7 @@ def run_bench(args, METRIC, UNIT):
                     {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(m * 8 + 320),
                      "note": "N>1: inputs replicated in HBM on every rank; result D2H inside the timed region"
                              + ("; " + main["e2e_note"] if main["e2e_note"] else "")}),
-            "gpu_launches": (9 if main["mode"] == 3 else 3) * args.steps * world,  # per rank: gather, score, solver (+6 building the compact copy)
+            "gpu_launches": (9 if main["mode"] in (3, 6) else 3) * args.steps * world,  # per rank: gather, score, solver (+6 building the compact copy)
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "kernel": "solver_kernel<float>, per GPU", "peak_source": peak_src},
         }

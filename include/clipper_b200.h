@@ -177,18 +177,19 @@ int clp_shard_import(clp_handle h, const void* blobs, int64_t blob_bytes_each, i
  * compact-row sweep). 1 lets two shards share one GPU, which is how the sharded path is exercised on
  * a single-GPU box. */
 int clp_set_ctas_per_sm(clp_handle h, int n);
-/* Cap on the TOTAL number of CTAs of the persistent solver / mat-vec kernels of this handle (0 = no cap: every
- * SM). A small problem (the reference's own use case is m <= 2000, benchmarks/main.cpp:206) cannot
- * fill 148 SMs and pays for device-wide barriers between hundreds of CTAs; with a cap of a few CTAs per handle,
- * many handles -- one per host thread, each on its own stream, like independent clipper::CLIPPER objects -- solve
- * side by side on disjoint SMs (clipper_b200/batch.py). */
+/* Cap on the TOTAL number of CTAs of the persistent solver / mat-vec kernels of this handle (0 = no cap: every SM).
+ * With clp_set_ctas_per_sm(h, 1) it lets the persistent kernels of several shards be co-resident on ONE GPU (the
+ * resident-vector kernel takes a whole SM's shared memory per CTA): the sharded code path on a single-GPU box. */
 int clp_set_grid_cap(clp_handle h, int n_ctas);
 /* How the solver / mat-vec sweep the matrix (the dense store always exists; getters read it):
- *   4 (default) auto: 3 when the graph is sparse enough for the compact copy to move fewer bytes than the
+ *   4 (default) auto: a compact copy (6, else 3) when the graph is sparse enough for it to move fewer bytes than the
  *     best dense sweep (x0.8), else 2 on an unsharded handle / 0 on a sharded one;
- *   3: compact copy -- after the dense build the non-neutral entries are packed as (fp32 value, 16-bit column
- *     offset) into a sliced-ELL layout (rows sorted by length inside every column segment, four at a time,
- *     interleaved in 4-entry chunks): 6 bytes per kept entry per objective evaluation;
+ *   6: compact copy + RESIDENT trial vector (m <= 27648): the non-neutral entries are packed as (fp32 value, 16-bit
+ *     column index) into a sliced-ELL layout over whole rows (rows sorted by length, four at a time, interleaved in
+ *     4-entry chunks); every CTA keeps the whole trial vector in shared memory and owns complete rows, so an
+ *     objective evaluation needs ONE device-wide synchronisation (clp_resident.cuh); 6 bytes per kept entry;
+ *   3: compact copy cut into column segments of <= 4096 (any m <= 262144): (fp32 value, 16-bit column offset),
+ *     same sliced-ELL layout per segment, two device-wide synchronisations per evaluation;
  *   2: column stripes, ONLY the upper triangle is read and every element is applied two-sidedly in-tile
  *     -> ~2 m^2 bytes per objective evaluation (fp32 storage), single GPU;
  *   1: column stripes, full matrix (4 m^2 bytes);
