@@ -16,6 +16,7 @@ from . import _capi
 from ._capi import ClipperError, STORE_F32, STORE_F64
 from .api import (CLIPPER, Params, Solution, Rounding, MCParams, SDPParams, invariants, utils, dsd,
                   __version__)
+from .batch import BatchCLIPPER
 
 __all__ = ["CLIPPER", "Params", "Solution", "Rounding", "MCParams", "SDPParams", "invariants", "utils",
-           "dsd", "ClipperError", "STORE_F32", "STORE_F64", "__version__"]
+           "dsd", "BatchCLIPPER", "ClipperError", "STORE_F32", "STORE_F64", "__version__"]

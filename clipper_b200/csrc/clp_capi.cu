@@ -153,6 +153,15 @@ int fail(clp_handle h, int code, const std::string& msg) {
 inline long long round_up(long long x, long long q) { return (x + q - 1) / q * q; }
 int reset_sync(clp_handle h);
 
+// nothing may propagate out of an extern "C" entry point (the library is loaded into Python and into C callers)
+template <typename F>
+int guarded(clp_handle h, F&& f) {
+  try { return f(); }
+  catch (const std::bad_alloc&) { return fail(h, CLP_ERR_ALLOC, "host allocation failed"); }
+  catch (const std::exception& e) { return fail(h, CLP_ERR_INVALID, std::string("internal error: ") + e.what()); }
+  catch (...) { return fail(h, CLP_ERR_INVALID, "internal error"); }
+}
+
 int ensure_pinned(clp_handle h, size_t bytes) {
   if (bytes <= h->pinned_cap) return CLP_OK;
   if (h->pinned) { cudaFreeHost(h->pinned); h->pinned = nullptr; h->pinned_cap = 0; }
@@ -505,7 +514,7 @@ int set_plan_for(clp_handle h, int mode) {
   return CLP_OK;
 }
 
-int finalize_matrix(clp_handle h) {
+int finalize_matrix_impl(clp_handle h) {
   int eff = h->dense_mode;
   if (eff == 3 || eff == 4 || eff == 6) {
     h->sp.plain = 0;
@@ -523,6 +532,8 @@ int finalize_matrix(clp_handle h) {
   if (eff == 1 || eff == 2) { if (int rc = build_plan2(h)) return rc; }
   return CLP_OK;
 }
+
+int finalize_matrix(clp_handle h) { return guarded(h, [&] { return finalize_matrix_impl(h); }); }
 
 // (re)allocate the matrix store for problem size m under the current shard config
 int ensure_matrix(clp_handle h, long long m) {
@@ -653,20 +664,23 @@ int score_from_host(clp_handle h, int kind, const double* D1, int d, long long n
   if (!h) return CLP_ERR_INVALID;
   if (!D1 || !D2 || d <= 0 || n1 <= 0 || n2 <= 0) return fail(h, CLP_ERR_INVALID, "bad data set arguments");
   CLP_CUDA(h, cudaSetDevice(h->device));
-  if (A == nullptr || m == 0) {  // all-to-all hypothesis (ref clipper.cpp:24, utils.h:61-71)
+  const bool all_to_all = (A == nullptr || m == 0);  // all-to-all hypothesis (ref clipper.cpp:24, utils.h:61-71)
+  if (all_to_all) {
     m = n1 * n2;
     if (m > (long long)kMaxSeg * kSegMax) return fail(h, CLP_ERR_INVALID, "all-to-all hypothesis too large");
-    h->A_host.resize((size_t)2 * m);
-    clp_create_all_to_all(n1, n2, h->A_host.data());
-  } else {
-    if (m < 0) return fail(h, CLP_ERR_INVALID, "negative m");
-    h->A_host.assign(A, A + (size_t)2 * m);
-  }
-  h->A_host_valid = true;
+  } else if (m < 0) return fail(h, CLP_ERR_INVALID, "negative m");
   CLP_CUDA(h, h->A_dev.ensure((size_t)2 * m * sizeof(int32_t)));
   CLP_CUDA(h, h->D1dev.ensure((size_t)d * n1 * sizeof(double)));
   CLP_CUDA(h, h->D2dev.ensure((size_t)d * n2 * sizeof(double)));
-  CLP_CUDA(h, cudaMemcpyAsync(h->A_dev.p, h->A_host.data(), (size_t)2 * m * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  if (all_to_all) {  // generated on the device: A never crosses PCIe; the host copy is fetched only if asked for
+    all_to_all_kernel<<<(unsigned)std::min<long long>((m + 255) / 256, 4096), 256, 0, h->stream>>>(n1, n2, h->A_dev.as<int32_t>());
+    CLP_CUDA(h, cudaGetLastError());
+    h->A_host_valid = false;
+  } else {
+    h->A_host.assign(A, A + (size_t)2 * m);
+    h->A_host_valid = true;
+    CLP_CUDA(h, cudaMemcpyAsync(h->A_dev.p, h->A_host.data(), (size_t)2 * m * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  }
   CLP_CUDA(h, cudaMemcpyAsync(h->D1dev.p, D1, (size_t)d * n1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CLP_CUDA(h, cudaMemcpyAsync(h->D2dev.p, D2, (size_t)d * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return score_on_device(h, kind, h->D1dev.as<double>(), d, n1, h->D2dev.as<double>(), n2,
@@ -676,11 +690,19 @@ int score_from_host(clp_handle h, int kind, const double* D1, int d, long long n
 int score_from_device(clp_handle h, int kind, const double* D1d, int d, long long n1, const double* D2d,
                       long long n2, const int32_t* Ad, long long m, double p0, double p1, double p2, double p3) {
   if (!h) return CLP_ERR_INVALID;
-  if (!D1d || !D2d || !Ad || d <= 0 || n1 <= 0 || n2 <= 0 || m <= 0)
-    return fail(h, CLP_ERR_INVALID, "bad device arguments (A_dev is required)");
+  if (!D1d || !D2d || d <= 0 || n1 <= 0 || n2 <= 0 || m < 0 || (Ad && m == 0))
+    return fail(h, CLP_ERR_INVALID, "bad device arguments");
   CLP_CUDA(h, cudaSetDevice(h->device));
+  if (!Ad) {  // all-to-all hypothesis, generated on the device
+    m = n1 * n2;
+    if (m > (long long)kMaxSeg * kSegMax) return fail(h, CLP_ERR_INVALID, "all-to-all hypothesis too large");
+  }
   CLP_CUDA(h, h->A_dev.ensure((size_t)2 * m * sizeof(int32_t)));
-  CLP_CUDA(h, cudaMemcpyAsync(h->A_dev.p, Ad, (size_t)2 * m * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  if (Ad) CLP_CUDA(h, cudaMemcpyAsync(h->A_dev.p, Ad, (size_t)2 * m * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  else {
+    all_to_all_kernel<<<(unsigned)std::min<long long>((m + 255) / 256, 4096), 256, 0, h->stream>>>(n1, n2, h->A_dev.as<int32_t>());
+    CLP_CUDA(h, cudaGetLastError());
+  }
   h->A_host_valid = false;
   return score_on_device(h, kind, D1d, d, n1, D2d, n2, h->A_dev.as<int32_t>(), m, p0, p1, p2, p3);
 }
@@ -958,19 +980,19 @@ int clp_set_stream(clp_handle h, void* cuda_stream) {
 // ---- scoring ------------------------------------------------------------------------------
 int clp_score_euclidean(clp_handle h, const double* D1, int32_t d, int64_t n1, const double* D2, int64_t n2,
                         const int32_t* A, int64_t m, double sigma, double epsilon, double mindist) {
-  return score_from_host(h, 0, D1, d, n1, D2, n2, A, m, sigma, epsilon, mindist, 0.0);
+  return guarded(h, [&] { return score_from_host(h, 0, D1, d, n1, D2, n2, A, m, sigma, epsilon, mindist, 0.0); });
 }
 int clp_score_pointnormal(clp_handle h, const double* D1, int64_t n1, const double* D2, int64_t n2,
                           const int32_t* A, int64_t m, double sigp, double epsp, double sign, double epsn) {
-  return score_from_host(h, 1, D1, 6, n1, D2, n2, A, m, sigp, epsp, sign, epsn);
+  return guarded(h, [&] { return score_from_host(h, 1, D1, 6, n1, D2, n2, A, m, sigp, epsp, sign, epsn); });
 }
 int clp_score_euclidean_dev(clp_handle h, const double* D1, int32_t d, int64_t n1, const double* D2, int64_t n2,
                             const int32_t* A, int64_t m, double sigma, double epsilon, double mindist) {
-  return score_from_device(h, 0, D1, d, n1, D2, n2, A, m, sigma, epsilon, mindist, 0.0);
+  return guarded(h, [&] { return score_from_device(h, 0, D1, d, n1, D2, n2, A, m, sigma, epsilon, mindist, 0.0); });
 }
 int clp_score_pointnormal_dev(clp_handle h, const double* D1, int64_t n1, const double* D2, int64_t n2,
                               const int32_t* A, int64_t m, double sigp, double epsp, double sign, double epsn) {
-  return score_from_device(h, 1, D1, 6, n1, D2, n2, A, m, sigp, epsp, sign, epsn);
+  return guarded(h, [&] { return score_from_device(h, 1, D1, 6, n1, D2, n2, A, m, sigp, epsp, sign, epsn); });
 }
 
 // ---- get / set ----------------------------------------------------------------------------
@@ -1090,7 +1112,7 @@ int clp_get_associations(clp_handle h, int32_t* A) {
   if (!h || !A) return CLP_ERR_INVALID;
   if (!h->has_A) return fail(h, CLP_ERR_INVALID, "no associations: the matrix was not built by scorePairwiseConsistency");
   if (!h->A_host_valid) {
-    h->A_host.resize((size_t)2 * h->m);
+    try { h->A_host.resize((size_t)2 * h->m); } catch (...) { return fail(h, CLP_ERR_ALLOC, "host allocation failed"); }
     CLP_CUDA(h, cudaSetDevice(h->device));
     CLP_CUDA(h, cudaMemcpyAsync(h->A_host.data(), h->A_dev.p, (size_t)2 * h->m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CLP_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1135,7 +1157,7 @@ int clp_solve(clp_handle h, const double* u0, clp_solution* out, double* u_out, 
   }
   if (u0_out) std::memcpy(u0_out, stage, (size_t)h->m * sizeof(double));
   CLP_CUDA(h, cudaMemcpyAsync(h->u0dev.p, stage, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  return solve_core(h, out, u_out, nullptr, nodes_out, t0);
+  return guarded(h, [&] { return solve_core(h, out, u_out, nullptr, nodes_out, t0); });
 }
 
 int clp_solve_dev(clp_handle h, const double* u0_dev, clp_solution* out, double* u_out_dev, int32_t* nodes_out) {
@@ -1144,7 +1166,7 @@ int clp_solve_dev(clp_handle h, const double* u0_dev, clp_solution* out, double*
   if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "solve() before any affinity matrix was scored or set");
   CLP_CUDA(h, cudaSetDevice(h->device));
   CLP_CUDA(h, cudaMemcpyAsync(h->u0dev.p, u0_dev, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  return solve_core(h, out, nullptr, u_out_dev, nodes_out, t0);
+  return guarded(h, [&] { return solve_core(h, out, nullptr, u_out_dev, nodes_out, t0); });
 }
 
 // ---- mat-vec ------------------------------------------------------------------------------
@@ -1329,6 +1351,272 @@ int clp_set_dense_mode(clp_handle h, int mode) {
     CLP_CUDA(h, cudaSetDevice(h->device));
     if (int rc = finalize_matrix(h)) return rc;
   }
+  return CLP_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// batches of small problems (clp_batch.cuh)
+// ==========================================================================================
+struct clp_batch_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  clp_params prm;
+  std::string err;
+  int sm_count = 0, smem_optin = 0;
+  DevBuf in_d1, in_d2, in_a, in_u0, out_u, probs, outs, nnz, sync, scratch;
+  void* pinned = nullptr; size_t pinned_cap = 0;
+  int last_ctas = 0; long long last_scratch = 0, last_nnz = 0;
+};
+
+namespace {
+thread_local std::string g_batch_create_error;
+int bfail(clp_batch b, int code, const std::string& msg) {
+  if (b) b->err = msg; else g_batch_create_error = msg;
+  return code;
+}
+#define CLP_BCUDA(b, call)                                                                 \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return bfail(b, e__ == cudaErrorMemoryAllocation ? CLP_ERR_ALLOC : CLP_ERR_CUDA,     \
+                   std::string(#call) + ": " + cudaGetErrorString(e__));                   \
+  } while (0)
+
+template <int KIND, int DD>
+int batch_launch(clp_batch b, BatchArgs& ba, int grid, size_t smem) {
+  CLP_BCUDA(b, cudaFuncSetAttribute(batch_solve_kernel<KIND, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  batch_solve_kernel<KIND, DD><<<grid, kBatchThreads, smem, b->stream>>>(ba);
+  CLP_BCUDA(b, cudaGetLastError());
+  return CLP_OK;
+}
+template <int KIND, int DD>
+int batch_occupancy(clp_batch b, size_t smem, int* occ) {
+  CLP_BCUDA(b, cudaFuncSetAttribute(batch_solve_kernel<KIND, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CLP_BCUDA(b, cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, batch_solve_kernel<KIND, DD>, kBatchThreads, smem));
+  return CLP_OK;
+}
+
+int batch_solve(clp_batch b, int kind, int dd, int32_t nprob, const double* const* D1, const int64_t* n1,
+                const double* const* D2, const int64_t* n2, const int32_t* const* A, const int64_t* m,
+                const double* const* u0, double p0, double p1, double p2, double p3, clp_solution* sols,
+                double* const* u_out, int32_t* const* nodes_out) {
+  if (!b) return CLP_ERR_INVALID;
+  if (nprob <= 0 || !D1 || !n1 || !D2 || !n2 || !m || !u0 || !sols) return bfail(b, CLP_ERR_INVALID, "bad batch arguments");
+  if (!((kind == 0 && (dd == 2 || dd == 3)) || (kind == 1 && dd == 6)))
+    return bfail(b, CLP_ERR_UNSUPPORTED, "batched scoring supports EuclideanDistance with d = 2, 3 and PointNormalDistance");
+  const clp_params& P = b->prm;
+  if (P.rounding == CLP_ROUND_DSD) return bfail(b, CLP_ERR_UNSUPPORTED, "Rounding::DSD is not available in a batch");
+  if (P.maxlsiters < 1) return bfail(b, CLP_ERR_INVALID, "maxlsiters must be >= 1");
+  const auto t_begin = std::chrono::steady_clock::now();
+  CLP_BCUDA(b, cudaSetDevice(b->device));
+  // ---- problem table and concatenated inputs
+  std::vector<BatchProblem> probs((size_t)nprob);
+  long long nd1 = 0, nd2 = 0, na = 0, nu = 0;
+  int max_m = 1;
+  for (int p = 0; p < nprob; ++p) {
+    BatchProblem& q = probs[(size_t)p];
+    if (!D1[p] || !D2[p] || !u0[p] || n1[p] <= 0 || n2[p] <= 0) return bfail(b, CLP_ERR_INVALID, "bad problem in the batch (null data or u0)");
+    const bool a2a = (A == nullptr || A[p] == nullptr || m[p] == 0);
+    const long long mp = a2a ? (long long)n1[p] * n2[p] : (long long)m[p];
+    if (mp <= 0 || mp > kBatchMaxM) return bfail(b, CLP_ERR_INVALID, "batched problems need 1 <= m <= 4096 associations");
+    q.d1_off = nd1; q.d2_off = nd2; q.a_off = a2a ? -1 : na; q.u_off = nu;
+    q.n1 = (int)n1[p]; q.n2 = (int)n2[p]; q.m = (int)mp; q.pad_ = 0;
+    nd1 += (long long)dd * n1[p]; nd2 += (long long)dd * n2[p]; if (!a2a) na += 2 * mp; nu += mp;
+    max_m = std::max(max_m, (int)mp);
+  }
+  const size_t bytes_in = (size_t)(nd1 + nd2 + nu) * 8 + (size_t)na * 4 + (size_t)nprob * sizeof(BatchProblem);
+  const size_t bytes_out = (size_t)nu * 8 + (size_t)nprob * (sizeof(SolverOut) + 4);
+  const size_t need = std::max(bytes_in, bytes_out) + 4096;
+  if (need > b->pinned_cap) {
+    if (b->pinned) { cudaFreeHost(b->pinned); b->pinned = nullptr; b->pinned_cap = 0; }
+    CLP_BCUDA(b, cudaMallocHost(&b->pinned, need));
+    b->pinned_cap = need;
+  }
+  char* hp = reinterpret_cast<char*>(b->pinned);
+  double* h_d1 = reinterpret_cast<double*>(hp);
+  double* h_d2 = h_d1 + nd1;
+  double* h_u0 = h_d2 + nd2;
+  int32_t* h_a = reinterpret_cast<int32_t*>(h_u0 + nu);
+  BatchProblem* h_pr = reinterpret_cast<BatchProblem*>(reinterpret_cast<char*>(h_a) + (((size_t)na * 4 + 15) & ~(size_t)15));
+  for (int p = 0; p < nprob; ++p) {
+    const BatchProblem& q = probs[(size_t)p];
+    std::memcpy(h_d1 + q.d1_off, D1[p], (size_t)dd * q.n1 * 8);
+    std::memcpy(h_d2 + q.d2_off, D2[p], (size_t)dd * q.n2 * 8);
+    std::memcpy(h_u0 + q.u_off, u0[p], (size_t)q.m * 8);
+    if (q.a_off >= 0) std::memcpy(h_a + q.a_off, A[p], (size_t)2 * q.m * 4);
+  }
+  std::memcpy(h_pr, probs.data(), (size_t)nprob * sizeof(BatchProblem));
+  CLP_BCUDA(b, b->in_d1.ensure((size_t)nd1 * 8 + 16));
+  CLP_BCUDA(b, b->in_d2.ensure((size_t)nd2 * 8 + 16));
+  CLP_BCUDA(b, b->in_u0.ensure((size_t)nu * 8 + 16));
+  CLP_BCUDA(b, b->in_a.ensure((size_t)na * 4 + 16));
+  CLP_BCUDA(b, b->out_u.ensure((size_t)nu * 8 + 16));
+  CLP_BCUDA(b, b->probs.ensure((size_t)nprob * sizeof(BatchProblem)));
+  CLP_BCUDA(b, b->outs.ensure((size_t)nprob * sizeof(SolverOut)));
+  CLP_BCUDA(b, b->nnz.ensure((size_t)nprob * 4 + 16));
+  CLP_BCUDA(b, cudaMemcpyAsync(b->in_d1.p, h_d1, (size_t)nd1 * 8, cudaMemcpyHostToDevice, b->stream));
+  CLP_BCUDA(b, cudaMemcpyAsync(b->in_d2.p, h_d2, (size_t)nd2 * 8, cudaMemcpyHostToDevice, b->stream));
+  CLP_BCUDA(b, cudaMemcpyAsync(b->in_u0.p, h_u0, (size_t)nu * 8, cudaMemcpyHostToDevice, b->stream));
+  if (na) CLP_BCUDA(b, cudaMemcpyAsync(b->in_a.p, h_a, (size_t)na * 4, cudaMemcpyHostToDevice, b->stream));
+  CLP_BCUDA(b, cudaMemcpyAsync(b->probs.p, h_pr, (size_t)nprob * sizeof(BatchProblem), cudaMemcpyHostToDevice, b->stream));
+  CLP_BCUDA(b, cudaMemsetAsync(b->nnz.p, 0, (size_t)nprob * 4 + 16, b->stream));
+  CLP_BCUDA(b, cudaMemsetAsync(b->outs.p, 0, (size_t)nprob * sizeof(SolverOut), b->stream));
+  CLP_BCUDA(b, cudaMemsetAsync(b->sync.p, 0, sizeof(SyncBlock), b->stream));
+  // ---- grid: as many CTAs as are co-resident (and as there are problems), each with its own scratch slot
+  const BatchSmem bs = batch_smem_plan(max_m);
+  if ((long long)bs.total > (long long)b->smem_optin) return bfail(b, CLP_ERR_UNSUPPORTED, "batch: shared memory plan exceeds the device limit");
+  int occ = 0;
+  int rc = (kind == 1) ? batch_occupancy<1, 6>(b, bs.total, &occ) : (dd == 3 ? batch_occupancy<0, 3>(b, bs.total, &occ) : batch_occupancy<0, 2>(b, bs.total, &occ));
+  if (rc) return rc;
+  if (occ < 1) return bfail(b, CLP_ERR_CUDA, "batch kernel does not fit an SM");
+  const BatchLayout L = batch_layout(max_m, dd);
+  size_t free_b = 0, total_b = 0;
+  CLP_BCUDA(b, cudaMemGetInfo(&free_b, &total_b));
+  const long long by_mem = (long long)((double)(free_b + b->scratch.cap) * 0.8 / (double)L.total);
+  int grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(nprob, (long long)occ * b->sm_count), by_mem));
+  CLP_BCUDA(b, b->scratch.ensure((size_t)grid * L.total));
+  BatchArgs ba;
+  std::memset(&ba, 0, sizeof(ba));
+  ba.prob = b->probs.as<BatchProblem>(); ba.nprob = nprob;
+  ba.D1 = b->in_d1.as<double>(); ba.D2 = b->in_d2.as<double>(); ba.A = b->in_a.as<int>(); ba.u0 = b->in_u0.as<double>();
+  ba.u_out = b->out_u.as<double>(); ba.out = b->outs.as<SolverOut>(); ba.nnz_out = b->nnz.as<unsigned int>();
+  ba.next = reinterpret_cast<int*>(&b->sync.as<SyncBlock>()->counts[0]);
+  ba.scratch = b->scratch.as<unsigned char>(); ba.scratch_stride = L.total;
+  ba.max_m = max_m; ba.kind = kind; ba.dd = dd;
+  ba.prm.tol_u = P.tol_u; ba.prm.tol_F = P.tol_F; ba.prm.beta = P.beta; ba.prm.eps = P.eps;
+  ba.prm.maxiniters = P.maxiniters; ba.prm.maxoliters = P.maxoliters; ba.prm.maxlsiters = P.maxlsiters;
+  ba.prm.rescale_u0 = P.rescale_u0 ? 1 : 0;
+  ba.p0 = p0; ba.p1 = p1; ba.p2 = p2; ba.p3 = p3; ba.affinityeps = P.affinityeps;
+  ba.sb = b->sync.as<SyncBlock>(); ba.spin_limit = 4LL * 1900000000LL;
+  CLP_BCUDA(b, cudaEventRecord(b->ev0, b->stream));
+  rc = (kind == 1) ? batch_launch<1, 6>(b, ba, grid, bs.total) : (dd == 3 ? batch_launch<0, 3>(b, ba, grid, bs.total) : batch_launch<0, 2>(b, ba, grid, bs.total));
+  if (rc) return rc;
+  CLP_BCUDA(b, cudaEventRecord(b->ev1, b->stream));
+  // ---- results
+  double* h_u = reinterpret_cast<double*>(hp);
+  SolverOut* h_out = reinterpret_cast<SolverOut*>(h_u + nu);
+  unsigned int* h_nnz = reinterpret_cast<unsigned int*>(h_out + nprob);
+  SyncBlock h_sb;
+  CLP_BCUDA(b, cudaMemcpyAsync(h_u, b->out_u.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, b->stream));
+  CLP_BCUDA(b, cudaMemcpyAsync(h_out, b->outs.p, (size_t)nprob * sizeof(SolverOut), cudaMemcpyDeviceToHost, b->stream));
+  CLP_BCUDA(b, cudaMemcpyAsync(h_nnz, b->nnz.p, (size_t)nprob * 4, cudaMemcpyDeviceToHost, b->stream));
+  CLP_BCUDA(b, cudaMemcpyAsync(&h_sb, b->sync.p, sizeof(SyncBlock), cudaMemcpyDeviceToHost, b->stream));
+  CLP_BCUDA(b, cudaStreamSynchronize(b->stream));
+  float ms = 0.f;
+  CLP_BCUDA(b, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  if (h_sb.error == 2) return bfail(b, CLP_ERR_INVALID, "association index out of range of D1/D2 in a batched problem");
+  if (h_sb.error != 0) return bfail(b, CLP_ERR_TIMEOUT, "batch kernel: an in-kernel wait timed out");
+  b->last_ctas = grid; b->last_scratch = (long long)grid * (long long)L.total; b->last_nnz = 0;
+  std::vector<int32_t> nodes;
+  for (int p = 0; p < nprob; ++p) {
+    const BatchProblem& q = probs[(size_t)p];
+    const SolverOut& so = h_out[p];
+    const double* u = h_u + q.u_off;
+    b->last_nnz += h_nnz[p] / 2;
+    nodes.clear();
+    if (P.rounding == CLP_ROUND_NONZERO) {
+      nodes.resize((size_t)q.m);
+      nodes.resize((size_t)clp_find_above(u, q.m, 0.0, nodes.data()));
+    } else {  // DSD_HEU, ref clipper.cpp:302-308
+      const int omega = (int)std::round(so.F);
+      if (omega >= 1) {
+        nodes.resize((size_t)std::min<long long>(omega, q.m));
+        nodes.resize((size_t)clp_find_k_largest(u, q.m, omega, nodes.data()));
+      }
+    }
+    clp_solution& s = sols[p];
+    std::memset(&s, 0, sizeof(s));
+    s.ifinal = so.ifinal; s.n_nodes = (int32_t)nodes.size(); s.score = so.F; s.d_final = so.d;
+    s.n_evals = so.n_evals; s.n_matvec = so.n_matvec; s.n_inner = so.n_inner; s.kernel_ms = ms;
+    s.prof_matvec_ms = 1e-6 * (double)so.ns_matvec; s.prof_combine_ms = 1e-6 * (double)so.ns_combine;
+    s.prof_exchange_ms = 1e-6 * (double)so.ns_exchange;
+    if (u_out && u_out[p]) std::memcpy(u_out[p], u, (size_t)q.m * 8);
+    if (nodes_out && nodes_out[p] && !nodes.empty()) std::memcpy(nodes_out[p], nodes.data(), nodes.size() * 4);
+  }
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  for (int p = 0; p < nprob; ++p) sols[p].t = wall / nprob;
+  return CLP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int clp_batch_create(int device, clp_batch* out) {
+  if (!out) return CLP_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return bfail(nullptr, CLP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return bfail(nullptr, CLP_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bfail(nullptr, CLP_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10) return bfail(nullptr, CLP_ERR_CUDA, "clipper_b200 is built for sm_100a only");
+  clp_batch b = new (std::nothrow) clp_batch_s();
+  if (!b) return bfail(nullptr, CLP_ERR_ALLOC, "host allocation failed");
+  b->device = device; b->sm_count = prop.multiProcessorCount;
+  clp_default_params(&b->prm);
+  auto bail = [&](const char* what, cudaError_t ce) {
+    g_batch_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    clp_batch_destroy(b);
+    return CLP_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&b->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&b->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = b->sync.ensure(sizeof(SyncBlock))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaDeviceGetAttribute(&b->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
+  *out = b;
+  return CLP_OK;
+}
+
+int clp_batch_destroy(clp_batch b) {
+  if (!b) return CLP_OK;
+  cudaSetDevice(b->device);
+  for (DevBuf* d : {&b->in_d1, &b->in_d2, &b->in_a, &b->in_u0, &b->out_u, &b->probs, &b->outs, &b->nnz, &b->sync, &b->scratch}) d->release();
+  if (b->pinned) cudaFreeHost(b->pinned);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+  return CLP_OK;
+}
+
+const char* clp_batch_last_error(clp_batch b) { return b ? b->err.c_str() : g_batch_create_error.c_str(); }
+
+int clp_batch_set_params(clp_batch b, const clp_params* p) {
+  if (!b || !p) return CLP_ERR_INVALID;
+  if (p->rounding < 0 || p->rounding > 2) return bfail(b, CLP_ERR_INVALID, "unknown rounding mode");
+  b->prm = *p;
+  return CLP_OK;
+}
+
+int clp_batch_solve_euclidean(clp_batch b, int32_t nprob, int32_t d, const double* const* D1, const int64_t* n1,
+                              const double* const* D2, const int64_t* n2, const int32_t* const* A, const int64_t* m,
+                              const double* const* u0, double sigma, double epsilon, double mindist,
+                              clp_solution* sols, double* const* u_out, int32_t* const* nodes_out) {
+  try { return batch_solve(b, 0, d, nprob, D1, n1, D2, n2, A, m, u0, sigma, epsilon, mindist, 0.0, sols, u_out, nodes_out); }
+  catch (const std::bad_alloc&) { return bfail(b, CLP_ERR_ALLOC, "host allocation failed"); }
+  catch (...) { return bfail(b, CLP_ERR_INVALID, "internal error"); }
+}
+
+int clp_batch_solve_pointnormal(clp_batch b, int32_t nprob, const double* const* D1, const int64_t* n1,
+                                const double* const* D2, const int64_t* n2, const int32_t* const* A, const int64_t* m,
+                                const double* const* u0, double sigp, double epsp, double sign, double epsn,
+                                clp_solution* sols, double* const* u_out, int32_t* const* nodes_out) {
+  try { return batch_solve(b, 1, 6, nprob, D1, n1, D2, n2, A, m, u0, sigp, epsp, sign, epsn, sols, u_out, nodes_out); }
+  catch (const std::bad_alloc&) { return bfail(b, CLP_ERR_ALLOC, "host allocation failed"); }
+  catch (...) { return bfail(b, CLP_ERR_INVALID, "internal error"); }
+}
+
+int clp_batch_info(clp_batch b, int32_t* n_ctas, int64_t* scratch_bytes, int64_t* nnz_upper_total) {
+  if (!b) return CLP_ERR_INVALID;
+  if (n_ctas) *n_ctas = b->last_ctas;
+  if (scratch_bytes) *scratch_bytes = b->last_scratch;
+  if (nnz_upper_total) *nnz_upper_total = b->last_nnz;
   return CLP_OK;
 }
 

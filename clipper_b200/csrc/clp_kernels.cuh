@@ -499,6 +499,16 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(ScoreArgs a) {
   }
 }
 
+// utils::createAllToAll (ref utils.h:61-71) on the device: association r = (r / n2, r % n2), column-major m x 2,
+// so the all-to-all hypothesis never crosses PCIe
+__global__ void all_to_all_kernel(long long n1, long long n2, int* A) {
+  const long long m = n1 * n2;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x) {
+    A[r] = (int)(r / n2);
+    A[m + r] = (int)(r % n2);
+  }
+}
+
 // E1[i][:] = D1[:, A(i,0)], E2[i][:] = D2[:, A(i,1)]; flags out-of-range association indices
 __global__ void gather_endpoints_kernel(const double* D1, const double* D2, const int* A0, const int* A1,
                                         int m, int d, long long n1, long long n2, double* E1, double* E2,
@@ -1368,3 +1378,4 @@ __global__ void gather_subblock_kernel(const T* M, long long ld, const int* S, i
 
 }  // namespace clp
 #include "clp_resident.cuh"
+#include "clp_batch.cuh"

@@ -291,19 +291,20 @@ __device__ __forceinline__ unsigned int res_item_of(const unsigned int* itemptr,
   return lo;
 }
 
-template <typename T, int NT, int U, int D, bool RING>
+// COH: the compact copy was written earlier IN THIS LAUNCH (batched problems): no ld.global.nc, L2-coherent loads instead
+template <typename T, int NT, int U, int D, bool RING, bool COH = false>
 __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, unsigned char* smem, const ResSmem& plan, int* errp) {
   constexpr int NW = NT / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SparseView& sp = a.sp;
   const unsigned int it0 = sp.cta_first[bid], it1 = sp.cta_first[bid + 1];
   if (it0 >= it1) return;
-  const unsigned int* __restrict__ itemptr = sp.itemptr;
+  const unsigned int* itemptr = sp.itemptr;
   const unsigned int c_lo = itemptr[it0], c_hi = itemptr[it1];
   const unsigned int s0 = res_warp_bound(c_lo, c_hi, warp, NW), s1 = res_warp_bound(c_lo, c_hi, warp + 1, NW);
   if (s0 >= s1) return;
-  const T* __restrict__ val = reinterpret_cast<const T*>(sp.val);
-  const unsigned short* __restrict__ idx = sp.off16;
+  const T* val = reinterpret_cast<const T*>(sp.val);
+  const unsigned short* idx = sp.off16;
   const unsigned int padk = (unsigned int)a.m | ((unsigned int)a.m << 16);  // column m holds 0.0
   double* pieces = a.pieces + ((size_t)bid * NW + warp) * kPieceVals;  // + item * 8
 
@@ -358,7 +359,7 @@ __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, uns
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const unsigned int c = lane + 32u * u;
-        if (c < n) E[s][u].load(val, idx, 4ull * (jb + c));
+        if (c < n) { if constexpr (COH) E[s][u].load_cg(val, idx, 4ull * (jb + c)); else E[s][u].load(val, idx, 4ull * (jb + c)); }
         else E[s][u].neutral_at(padk);
       }
     };
@@ -525,7 +526,7 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
 // ---------------------------------------------------------------------------------------------------------------
 // the solver body (shared by solver_resident_kernel and the batched kernel)
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int NT, int U, int D, bool RING, bool SHARDED, bool SOLO>
+template <typename T, int NT, int U, int D, bool RING, bool SHARDED, bool SOLO, bool COH = false>
 __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   constexpr int NW = NT / 32;
   const int bid = SOLO ? 0 : (int)blockIdx.x;  // CTA index within the problem (batched: one CTA per problem)
@@ -585,7 +586,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   if (!res_exchange<NT, SHARDED, SOLO>(a, bid, loc, vals, red_par, round, seq, red_s, fin)) { status = 5; goto finish; } \
   RES_LAP(ns_ex);
 #define RES_SWEEP()                                                                                 \
-  res_sweep<T, NT, U, D, RING>(a, bid, vs, smem, plan, errp);                                            \
+  res_sweep<T, NT, U, D, RING, COH>(a, bid, vs, smem, plan, errp);                                       \
   ++n_matvec;                                                                                       \
   __syncthreads();                                                                                  \
   RES_LAP(ns_mv);

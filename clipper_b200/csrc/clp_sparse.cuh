@@ -93,7 +93,7 @@ __global__ void sparse_count_kernel(const T* M, long long ld, int m, int rows, i
 }
 
 // pass 2: one block (1024 threads) per column segment sorts the rows by slice length, longest first (counting sort
-// over the nb = W/4 + 2 possible lengths in chunks; ties in arrival order, which does not influence any result).
+// over the nb = W/4 + 2 possible lengths in chunks; ties in row order: a stable sort, so the layout is reproducible).
 //   rowid[seg][pos] = row at sorted position pos, rank[seg][row] = its position
 // Dynamic shared memory: (nb + 1) counters.
 __global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, int nb, unsigned int* rowid, unsigned int* rank,
@@ -136,10 +136,29 @@ __global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, int nb,
     }
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) {
-    const unsigned int pos = atomicAdd(&hist[min((c[r] + 3u) >> 2, (unsigned int)(nb - 1))], 1u);
-    rowid[(size_t)blockIdx.x * rows_pad + pos] = (unsigned int)r;
-    rank[(size_t)blockIdx.x * rows_pad + r] = pos;
+  // STABLE placement (ties in row order): the layout -- hence the grouping of every fp64 sum downstream -- must not
+  // depend on the arrival order of atomics, or two runs on the same input differ in the last bit.  Rows are taken in
+  // tiles of blockDim.x in row order; inside a tile the warps take turns (one __syncthreads per turn); inside a warp
+  // __match_any_sync ranks the lanes of equal length class.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int base = 0; base < rows_pad; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    const bool have = r < rows_pad;
+    const unsigned int cls = have ? min((c[r] + 3u) >> 2, (unsigned int)(nb - 1)) : 0xffffffffu;
+    const unsigned int peers = __match_any_sync(0xffffffffu, cls);
+    const int leader = __ffs(peers) - 1;
+    const unsigned int before = __popc(peers & ((1u << lane) - 1u));
+    unsigned int start = 0u;
+    for (int w = 0; w < nwarp; ++w) {
+      if (warp == w && have && lane == leader) { start = hist[cls]; hist[cls] = start + __popc(peers); }
+      __syncthreads();
+    }
+    start = __shfl_sync(0xffffffffu, start, leader);
+    if (have) {
+      const unsigned int pos = start + before;
+      rowid[(size_t)blockIdx.x * rows_pad + pos] = (unsigned int)r;
+      rank[(size_t)blockIdx.x * rows_pad + r] = pos;
+    }
   }
 }
 
@@ -262,28 +281,16 @@ __global__ void sparse_fill_kernel(const T* M, long long ld, int m, int rows, in
 // stores that each touch a different sector).
 constexpr int kFillWarps = 4;
 constexpr int kRing = 256;  // entries per member ring: < 36 left after a flush + <= 128 new ones per step
+// one warp: the item whose chunks are [b, e) of the stream and whose members are rows r[0..3]; columns [c0, c1)
 template <typename T>
-__global__ void __launch_bounds__(kFillWarps * 32)
-sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
-                         const unsigned int* itemptr, const unsigned int* rowid, T* val, unsigned short* off16,
-                         int off_shift /* 3: byte offset of v[col] in the staged segment; 0: column index */,
-                         unsigned int pad_off /* offset stored in padding entries: a slot that holds 0.0 */) {
-  __shared__ __align__(16) T ringv[kFillWarps][4][kRing];
-  __shared__ __align__(8) unsigned short ringo[kFillWarps][4][kRing];
-  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NI = rows_pad >> 2;
-  const long long gw = (long long)blockIdx.x * kFillWarps + wic;
-  if (gw >= (long long)nseg * NI) return;
-  const int seg = (int)(gw / NI), it = (int)(gw - (long long)seg * NI);
-  const unsigned int b = itemptr[(size_t)seg * (NI + 1) + it], e = itemptr[(size_t)seg * (NI + 1) + it + 1];
+__device__ __forceinline__ void sell_fill_item_warp(const T* M, long long ld, int rows, int c0, int c1, unsigned int b, unsigned int e,
+                                                    const unsigned int (&r)[4], T* val, unsigned short* off16, int off_shift,
+                                                    unsigned int pad_off, T (*rv)[kRing], unsigned short (*ro)[kRing]) {
+  const int lane = threadIdx.x & 31;
   const unsigned int L = (e - b) >> 2;  // chunks per member
   if (L == 0u) return;
-  unsigned int r[4], n[4] = {0u, 0u, 0u, 0u}, f[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-  for (int s_ = 0; s_ < 4; ++s_) r[s_] = rowid[(size_t)seg * rows_pad + 4 * it + s_];
+  unsigned int n[4] = {0u, 0u, 0u, 0u}, f[4] = {0u, 0u, 0u, 0u};
   const int g = lane >> 2, ms = lane & 3;  // flush role: chunk f + g of member ms
-  T (*rv)[kRing] = ringv[wic];
-  unsigned short (*ro)[kRing] = ringo[wic];
   // writes chunk k of member ms (entries beyond the member's n are neutral padding)
   auto put_chunk = [&](unsigned int k, unsigned int nm) {
     T x[4]; unsigned short o[4];
@@ -298,7 +305,6 @@ sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad
     Quad<T>::store(val + at, x);
     *reinterpret_cast<uint2*>(off16 + at) = make_uint2((unsigned int)o[0] | ((unsigned int)o[1] << 16), (unsigned int)o[2] | ((unsigned int)o[3] << 16));
   };
-  const int c0 = seg * W, c1 = min(m, c0 + W);
   for (int j0 = c0; j0 < c1; j0 += 128) {
     const int j = j0 + lane * 4;
 #pragma unroll
@@ -347,6 +353,28 @@ sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad
     const unsigned int fm = ms == 0 ? f[0] : ms == 1 ? f[1] : ms == 2 ? f[2] : f[3];
     for (unsigned int k = fm + g; k < L; k += 8u) put_chunk(k, nm);
   }
+  __syncwarp();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFillWarps * 32)
+sparse_fill_items_kernel(const T* M, long long ld, int m, int rows, int rows_pad, int W, int nseg,
+                         const unsigned int* itemptr, const unsigned int* rowid, T* val, unsigned short* off16,
+                         int off_shift /* 3: byte offset of v[col] in the staged segment; 0: column index */,
+                         unsigned int pad_off /* offset stored in padding entries: a slot that holds 0.0 */) {
+  __shared__ __align__(16) T ringv[kFillWarps][4][kRing];
+  __shared__ __align__(8) unsigned short ringo[kFillWarps][4][kRing];
+  const int wic = threadIdx.x >> 5;
+  const int NI = rows_pad >> 2;
+  const long long gw = (long long)blockIdx.x * kFillWarps + wic;
+  if (gw >= (long long)nseg * NI) return;
+  const int seg = (int)(gw / NI), it = (int)(gw - (long long)seg * NI);
+  const unsigned int b = itemptr[(size_t)seg * (NI + 1) + it], e = itemptr[(size_t)seg * (NI + 1) + it + 1];
+  unsigned int r[4];
+#pragma unroll
+  for (int s_ = 0; s_ < 4; ++s_) r[s_] = rowid[(size_t)seg * rows_pad + 4 * it + s_];
+  const int c0 = seg * W, c1 = min(m, c0 + W);
+  sell_fill_item_warp<T>(M, ld, rows, c0, c1, b, e, r, val, off16, off_shift, pad_off, ringv[wic], ringo[wic]);
 }
 
 // 4 entries of one row slice
@@ -356,6 +384,10 @@ template <> struct Entry4<float> {
   __device__ __forceinline__ void load(const float* val, const unsigned short* off, unsigned long long at) {
     x = ldg_stream(reinterpret_cast<const float4*>(val + at));
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(off + at));
+  }
+  __device__ __forceinline__ void load_cg(const float* val, const unsigned short* off, unsigned long long at) {  // L2-coherent
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(val + at));
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(off + at));
   }
   __device__ __forceinline__ float get(int e) const { return e == 0 ? x.x : e == 1 ? x.y : e == 2 ? x.z : x.w; }
   __device__ __forceinline__ void neutral() { x = make_float4(-0.f, -0.f, -0.f, -0.f); k = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16)); }
@@ -370,6 +402,11 @@ template <> struct Entry4<double> {
     a = ldg_stream(reinterpret_cast<const double2*>(val + at));
     b = ldg_stream(reinterpret_cast<const double2*>(val + at) + 1);
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(off + at));
+  }
+  __device__ __forceinline__ void load_cg(const double* val, const unsigned short* off, unsigned long long at) {
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(a.x), "=d"(a.y) : "l"(val + at));
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(b.x), "=d"(b.y) : "l"(val + at + 2));
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(k.x), "=r"(k.y) : "l"(off + at));
   }
   __device__ __forceinline__ double get(int e) const { return e == 0 ? a.x : e == 1 ? a.y : e == 2 ? b.x : b.y; }
   __device__ __forceinline__ void neutral() { a = make_double2(-0.0, -0.0); b = a; k = make_uint2(kZeroSlot | (kZeroSlot << 16), kZeroSlot | (kZeroSlot << 16)); }

@@ -96,7 +96,8 @@ const char* clp_version(void);
 
 /* ---- K1: scorePairwiseConsistency (clipper.cpp:21-65) ----------------------------------- */
 /* EuclideanDistance (src/invariants/euclidean_distance.cpp:13-31). A==NULL or m==0 ->
- * all-to-all hypothesis (utils.h:61-71). Host pointers; copies in, builds dense M/C in HBM. */
+ * all-to-all hypothesis (utils.h:61-71), generated on the device (A never crosses PCIe; clp_get_associations
+ * fetches it on demand). Host pointers; copies in, builds dense M/C in HBM. */
 int clp_score_euclidean(clp_handle h, const double* D1, int32_t d, int64_t n1, const double* D2,
                         int64_t n2, const int32_t* A, int64_t m, double sigma, double epsilon,
                         double mindist);
@@ -104,7 +105,8 @@ int clp_score_euclidean(clp_handle h, const double* D1, int32_t d, int64_t n1, c
 int clp_score_pointnormal(clp_handle h, const double* D1, int64_t n1, const double* D2, int64_t n2,
                           const int32_t* A, int64_t m, double sigp, double epsp, double sign,
                           double epsn);
-/* Same, inputs already resident in HBM (device pointers, same layouts). A_dev must be given. */
+/* Same, inputs already resident in HBM (device pointers, same layouts). A_dev == NULL: all-to-all hypothesis
+ * (m is then ignored and becomes n1 * n2). */
 int clp_score_euclidean_dev(clp_handle h, const double* D1_dev, int32_t d, int64_t n1,
                             const double* D2_dev, int64_t n2, const int32_t* A_dev, int64_t m,
                             double sigma, double epsilon, double mindist);
@@ -198,6 +200,33 @@ int clp_set_dense_mode(clp_handle h, int mode);
 int clp_get_dense_mode(clp_handle h, int* requested, int* effective);
 /* entries kept by the compact copy (all local rows) and the algorithmic bytes one sparse pass reads */
 int clp_sparse_info(clp_handle h, int64_t* nnz_kept, int64_t* bytes_per_pass);
+
+/* ---- batches of small problems: hundreds of registrations in ONE launch ------------------------
+ * The reference's benchmark solves its m <= 2048 problems one after the other (benchmarks/main.cpp:254-270: a fresh
+ * clipper::CLIPPER, scorePairwiseConsistency, solve per trial).  A batch handle takes the whole list: ONE CTA per
+ * problem scores the pairs, builds the compact copy and runs findDenseClique without any device-wide synchronisation;
+ * the CTAs of a persistent grid draw problems from a counter.  Every problem gives the result the single-problem
+ * path gives for it (same kernels' arithmetic).  Rounding: NONZERO and DSD_HEU (the default); Rounding::DSD is not
+ * available in a batch (CLP_ERR_UNSUPPORTED).  m <= 4096 per problem.
+ * Arrays of nprob host pointers / sizes; A[p] == NULL -> all-to-all hypothesis for problem p; u0[p] must be given
+ * (m[p] doubles).  sols[p] receives ifinal, score, d_final, n_evals, n_matvec, n_inner, n_nodes; u_out[p] (m[p] doubles)
+ * and nodes_out[p] (m[p] int32) may be NULL pointers / NULL arrays.  kernel_ms of every sols[p] is the device time of
+ * the whole batch launch, t the wall-clock time of the call divided by nprob. */
+typedef struct clp_batch_s* clp_batch;
+int clp_batch_create(int device, clp_batch* out);
+int clp_batch_destroy(clp_batch b);
+const char* clp_batch_last_error(clp_batch b); /* b may be NULL: error of the last failed clp_batch_create */
+int clp_batch_set_params(clp_batch b, const clp_params* p);
+int clp_batch_solve_euclidean(clp_batch b, int32_t nprob, int32_t d, const double* const* D1, const int64_t* n1,
+                              const double* const* D2, const int64_t* n2, const int32_t* const* A, const int64_t* m,
+                              const double* const* u0, double sigma, double epsilon, double mindist,
+                              clp_solution* sols, double* const* u_out, int32_t* const* nodes_out);
+int clp_batch_solve_pointnormal(clp_batch b, int32_t nprob, const double* const* D1, const int64_t* n1,
+                                const double* const* D2, const int64_t* n2, const int32_t* const* A, const int64_t* m,
+                                const double* const* u0, double sigp, double epsp, double sign, double epsn,
+                                clp_solution* sols, double* const* u_out, int32_t* const* nodes_out);
+/* diagnostics of the last batch: CTAs of the launch, HBM scratch bytes, stored affinities (i<j) over all problems */
+int clp_batch_info(clp_batch b, int32_t* n_ctas, int64_t* scratch_bytes, int64_t* nnz_upper_total);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""problems/s of batches of small problems (reference benchmarks/main.cpp:206-208: m in {64 ... 2048}):
+the one-launch batch path against (a) the single-problem GPU path called in a loop and (b) the CPU oracle run
+one-problem-per-core on all host cores (the fair CPU shape for independent problems).  One JSON line per size."""
+import json
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make(m, k, rho=0.9):
+    from clipper_b200 import datagen
+    prob = datagen.euclidean_problem(m, rho, 9000 + 13 * m + k)
+    A = prob["A"]
+    used1, inv1 = np.unique(A[:, 0], return_inverse=True)
+    used2, inv2 = np.unique(A[:, 1], return_inverse=True)
+    return dict(D1=np.asfortranarray(prob["D1"][:, used1]), D2=np.asfortranarray(prob["D2"][:, used2]),
+                A=np.asfortranarray(np.stack([inv1, inv2], axis=1).astype(np.int32)), u0=prob["u0"])
+
+
+def oracle_one(p):
+    from oracle import clipper_oracle as orc
+    o = orc.Oracle(); o.score_euclidean(p["D1"], p["D2"], p["A"], sigma=0.015, epsilon=0.05, nthreads=1)
+    s = o.solve(p["u0"])
+    return float(s.score), len(s.nodes)
+
+
+def main():
+    import clipper_b200 as clp
+    sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "64,256,512,1024,2048".split(","))]
+    nprob = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+    cores = len(os.sched_getaffinity(0))
+    ip = clp.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = 0.015, 0.05
+    for m in sizes:
+        n = nprob if m <= 1024 else max(64, nprob // 2)
+        distinct = [make(m, k) for k in range(min(n, 32))]
+        probs = [distinct[k % len(distinct)] for k in range(n)]
+        b = clp.BatchCLIPPER(clp.invariants.EuclideanDistance(ip), clp.Params())
+        b.solve_many(probs[:8])
+        t0 = time.perf_counter(); sols = b.solve_many(probs); t_batch = time.perf_counter() - t0
+        kms = sols[0].kernel_ms
+        c = clp.CLIPPER(clp.invariants.EuclideanDistance(ip), clp.Params())
+        nl = min(n, 64)
+        for p in probs[:2]:
+            c.score_pairwise_consistency(p["D1"], p["D2"], p["A"]); c.solve(p["u0"])
+        t0 = time.perf_counter()
+        for p in probs[:nl]:
+            c.score_pairwise_consistency(p["D1"], p["D2"], p["A"]); c.solve(p["u0"])
+        t_loop = (time.perf_counter() - t0) / nl
+        ncpu = min(n, max(cores, 16) * (2 if m <= 512 else 1))
+        with ProcessPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(oracle_one, probs[:cores]))  # warm the pool
+            t0 = time.perf_counter(); ref = list(ex.map(oracle_one, probs[:ncpu], chunksize=1)); t_cpu = time.perf_counter() - t0
+        same = all(abs(r[0] - s.score) <= 1e-5 * max(1, abs(r[0])) and r[1] == len(s.nodes) for r, s in zip(ref, sols))
+        ctas, scratch, nnz = b.info()
+        print(json.dumps(dict(m=m, problems=n, batch_problems_per_s=n / t_batch, batch_kernel_problems_per_s=n / (kms * 1e-3),
+                              batch_kernel_ms=kms, single_path_loop_problems_per_s=1.0 / t_loop,
+                              cpu_oracle_problems_per_s=ncpu / t_cpu, cpu_cores=cores, cpu_problems=ncpu,
+                              speedup_vs_cpu_box=(n / t_batch) / (ncpu / t_cpu), speedup_vs_single_loop=(n / t_batch) * t_loop,
+                              same_as_oracle=same, ctas=ctas, scratch_GB=scratch / 1e9, density=nnz / (n * m * (m - 1) / 2),
+                              mean_evals=float(np.mean([s.n_evals for s in sols])))), flush=True)
+
+
+if __name__ == "__main__":
+    main()
