@@ -319,6 +319,11 @@ def run_ours(args):
                "same_inlier_set": sorted(info["nodes"]) == sorted(nodes_dev),
                "rel_dF": abs(info["score"] - F_dev) / abs(info["score"])}
 
+    # ---- BASELINE config 4 (m = 80000) on this one GPU: the N = 1 anchor of the row-sharded scaling runs
+    config4 = None
+    if not args.no_config4 and args.workload == "c2" and args.m is None:
+        config4 = run_config4(clipperpy, _capi, L, dev, stream, max(1, min(3, args.steps)))
+
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -359,7 +364,50 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if config4:
+        line["config4"] = config4
     print(json.dumps(line))
+
+
+def run_config4(clipperpy, _capi, L, dev, stream, steps):
+    """m = 80000 (BASELINE config 4) unsharded: device-timed steps with inputs resident in HBM, same metric"""
+    import torch
+    from clipper_b200 import datagen
+    prob = datagen.config_problem("c4"); cfg = prob["cfg"]; m = cfg["m"]
+    ip = clipperpy.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = cfg["sigma"], cfg["epsilon"]
+    clip = clipperpy.CLIPPER(clipperpy.invariants.EuclideanDistance(ip), clipperpy.Params(), device=dev.index)
+    h = clip.handle
+    clip.set_stream(stream.cuda_stream)
+    D1 = torch.from_numpy(np.ascontiguousarray(prob["D1"].T)).to(dev)
+    D2 = torch.from_numpy(np.ascontiguousarray(prob["D2"].T)).to(dev)
+    A = torch.from_numpy(np.ascontiguousarray(prob["A"].T)).to(dev)
+    u0 = torch.from_numpy(prob["u0"]).to(dev)
+    u_out = torch.empty_like(u0)
+    nodes = np.zeros(m, np.int32)
+    sol = _capi.ClpSolution()
+
+    def step():
+        _capi.check(h, L.clp_score_euclidean_dev(h, D1.data_ptr(), 3, D1.shape[0], D2.data_ptr(), D2.shape[0], A.data_ptr(), m,
+                                                 cfg["sigma"], cfg["epsilon"], 0.0))
+        _capi.check(h, L.clp_solve_dev(h, u0.data_ptr(), C.byref(sol), u_out.data_ptr(), nodes.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    kms = []
+    for _ in range(steps):
+        step(); kms.append(sol.kernel_ms)
+    ev1.record(stream); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    mode = clip.dense_mode()
+    kept, pass_bytes = clip.sparse_info() if mode in (3, 6) else (None, 4 * m * m)
+    return {"workload": workload_name("c4", cfg), "value": m * steps / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "ms_per_step": ms / steps, "solver_kernel_ms": float(np.mean(kms)), "evals": int(sol.n_evals), "sweep_mode": mode,
+            "kept_entries": kept, "per_gpu_gbs": sol.n_matvec * pass_bytes / (float(np.mean(kms)) * 1e-3) / 1e9,
+            "F": sol.score, "n_nodes": int(sol.n_nodes),
+            "note": "unsharded anchor of the N-GPU runs; the CPU oracle at this size (about 5 min, single-threaded solver "
+                    "like the reference) is timed by tests/test_gpu_fullsize.py::test_full_size_c4_vs_oracle"}
 
 
 FUSED_COUNT = os.environ.get("CLP_FUSE_COUNT", "1") != "0" and os.environ.get("CLP_SCORE_FILTER", "1") != "0"
@@ -374,7 +422,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--m", type=int, default=None, help="override the workload's m (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-config4", action="store_true", help="N>1: skip the extra m=80000 measurement")
+    ap.add_argument("--no-config4", action="store_true", help="skip the extra m=80000 (BASELINE config 4) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -307,8 +307,8 @@ def run_bench(args, METRIC, UNIT):
         #      the device-timed line.
         e2e_ms, e2e_note, h2d = None, None, 0
         try:
-            if os.environ.get("CLP_BENCH_E2E_MULTI") != "1":  # opt-in until it has run once on a multi-GPU box
-                raise RuntimeError("not requested (CLP_BENCH_E2E_MULTI=1)")
+            if os.environ.get("CLP_BENCH_E2E_MULTI") == "0":
+                raise RuntimeError("disabled (CLP_BENCH_E2E_MULTI=0)")
             hD1 = torch.from_numpy(np.ascontiguousarray(prob["D1"].T)).pin_memory()
             hD2 = torch.from_numpy(np.ascontiguousarray(prob["D2"].T)).pin_memory()
             hA = torch.from_numpy(np.ascontiguousarray(prob["A"].T)).pin_memory()

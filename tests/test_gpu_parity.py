@@ -441,8 +441,9 @@ def test_full_size_c2_properties(clp):
 @pytest.mark.parametrize("m", [7, 100, 2047, 2049, 4500, 6200])
 def test_dense_modes_agree(clp, orc, m, storage):
     """mode 2 reads only the upper triangle (two-sided in-tile update); modes 1 / 0 read the full matrix;
-    mode 3 sweeps the compact-row copy; 4 picks automatically.  Sizes straddle the 2048-column stripe
-    boundary, the diagonal-block logic and the 128-column segment steps."""
+    mode 3 sweeps the segmented compact copy, mode 6 the full-row compact copy with the resident trial vector
+    (another kernel: one synchronisation per evaluation); 4 picks automatically (= 6 at these sizes).  Sizes straddle
+    the 2048-column stripe boundary, the diagonal-block logic and the 128-column segment steps."""
     from clipper_b200 import datagen
     prob = datagen.config_problem("c2", m); cfg = prob["cfg"]
     o = orc.Oracle()
@@ -451,21 +452,29 @@ def test_dense_modes_agree(clp, orc, m, storage):
     rng = np.random.default_rng(m)
     v = rng.random(m)
     res = []
-    for mode in (0, 1, 2, 3, 4):
+    modes = (0, 1, 2, 3, 6, 4)
+    effective = []
+    for mode in modes:
         c = make_euclid(clp, sigma=cfg["sigma"], epsilon=cfg["epsilon"], storage=storage)
         c.set_dense_mode(mode)
         c.score_pairwise_consistency(prob["D1"], prob["D2"], prob["A"])
+        effective.append(c.dense_mode())
         y, Mv, Cv = c.matvec(v, 0.6)
         c.solve(prob["u0"]); s = c.get_solution()
         res.append((y, Mv, Cv, s))
-    for k in (1, 2, 3, 4):
+    assert effective[:5] == [0, 1, 2, 3, 6] and effective[5] in (2, 6)
+    for k in range(1, len(modes)):
         assert np.abs(res[k][1] - res[0][1]).max() <= 1e-12 * max(1.0, np.abs(res[0][1]).max())
         assert np.abs(res[k][2] - res[0][2]).max() <= 1e-12 * max(1.0, np.abs(res[0][2]).max())
         assert np.abs(res[k][0] - res[0][0]).max() <= 1e-12 * max(1.0, np.abs(res[0][0]).max())
         s0, sk = res[0][3], res[k][3]
         assert sk.nodes == s0.nodes and sk.ifinal == s0.ifinal and sk.n_evals == s0.n_evals
-        assert abs(sk.score - s0.score) <= 1e-12 * abs(s0.score)
-        assert np.abs(sk.u - s0.u).max() <= 1e-12
+        # the segmented kernels share every O(m) statement and differ only in how a row's products are grouped; the
+        # resident kernel also groups the scalar reductions differently, so its trajectory agrees to rounding (1e-12 per
+        # step) and its final objective to well below the solver's own stopping tolerance tol_F = 1e-9
+        same_kernel = effective[k] in (0, 1, 2, 3)
+        assert abs(sk.score - s0.score) <= (1e-12 if same_kernel else 2e-11) * abs(s0.score)
+        assert np.abs(sk.u - s0.u).max() <= (1e-12 if same_kernel else 1e-10)
     for _, _, _, s in res:
         assert sorted(s.nodes) == sorted(so.nodes.tolist())
         assert abs(s.score - so.score) <= (1e-9 if storage == 1 else 1e-5) * abs(so.score)
