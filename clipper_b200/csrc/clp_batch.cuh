@@ -87,6 +87,7 @@ struct BatchArgs {
   SolverOut* out;          // [nprob]
   unsigned int* nnz_out;   // [nprob] kept entries (i != j, both triangles) -- diagnostics
   int* next;               // problem counter
+  unsigned long long* prof;  // nullable: [nprob][4] ns spent in gather+score, build, solve, whole problem -- diagnostics
   unsigned char* scratch; size_t scratch_stride;
   int max_m, kind, dd;     // kind 0: EuclideanDistance (dd = 2, 3), 1: PointNormalDistance (dd = 6)
   SolverParams prm;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
     const int p = s_p;
     if (p >= ba.nprob) break;
     const BatchProblem P = ba.prob[p];
+    const unsigned long long t_begin = global_ns();
     const int m = P.m;
     const int ld = (m + 127) / 128 * 128;
     const int rows_pad = (m + 3) / 4 * 4;
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
     }
     __syncthreads();
 
+    const unsigned long long t_scored = global_ns();
     // ---- 3. full-row sliced-ELL copy: sort rows by length (longest first), items of four, scan, fill
     const int nb = ld / 4 + 2;
     unsigned int* hist = reinterpret_cast<unsigned int*>(smem + bs.hist);                         // [nb + 1]
@@ -347,11 +350,17 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
       a.out = ba.out + p;
       a.rank = 0; a.world = 1;
       for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = nullptr; a.peer_comm[r] = nullptr; }
-      a.comm = nullptr; a.seq0 = 0; a.spin_limit = ba.spin_limit; a.ring_stages = 0;
+      a.comm = nullptr; a.seq0 = 0; a.spin_limit = ba.spin_limit; a.ring_stages = 0; a.smem_bytes = 0u; a.prof_cta = nullptr;
       sa = a;
     }
     __syncthreads();
+    const unsigned long long t_built = global_ns();
     res_solve_body<float, kBatchThreads, kBatchU, kBatchD, false, false, true, /*coherent loads*/ true>(sa, smem);
+    if (ba.prof && tid == 0) {
+      const unsigned long long t_end = global_ns();
+      ba.prof[(size_t)p * 4 + 0] = t_scored - t_begin; ba.prof[(size_t)p * 4 + 1] = t_built - t_scored;
+      ba.prof[(size_t)p * 4 + 2] = t_end - t_built; ba.prof[(size_t)p * 4 + 3] = t_end - t_begin;
+    }
   }
 }
 

@@ -94,6 +94,9 @@ struct clp_handle_s {
   int res_enabled = env_int("CLP_RESIDENT", 1);
   int res_cfg = env_int("CLP_RES_CFG", -1);         // load pipeline of the resident sweep (-1: automatic), see kResCfgs
   int res_cfg_eff = 0;
+  int res_smem_extra = env_int("CLP_RES_SMEM_EXTRA", 1);  // 0: launch with the plan's minimum (piece table / row state in HBM)
+  int prof_ctas = env_int("CLP_PROF_CTAS", 0);      // print the per-CTA phase times of every resident solve (stderr)
+  DevBuf prof_buf;
   int res_G = 0;                                    // CTAs of the resident kernels for the current matrix
   int res_NI = 0;
   bool compact_resident = false;                    // layout of the current compact copy: full rows + column indices
@@ -305,9 +308,14 @@ auto res_dispatch(int c, F&& f) {
   }
 }
 
-unsigned int res_smem_bytes(clp_handle h, int c) {
+unsigned int res_smem_bytes(clp_handle h, int c) {  // the plan's minimum
   const ResCfg& k = kResCfgs[c];
   return res_smem_plan((int)h->m, k.NT / 32, k.ring ? k.D : 0, k.U, (int)h->esize()).total;
+}
+// what the resident kernels are launched with: everything an SM offers (one CTA per SM anyway); the part beyond the
+// plan's minimum keeps the CTA's piece table and per-row solver state on chip
+unsigned int res_launch_smem(clp_handle h, int c) {
+  return std::max(res_smem_bytes(h, c), (unsigned int)std::max(0, h->res_smem_extra ? h->smem_optin : 0));
 }
 
 // can the resident solver take a problem of this size on this handle?
@@ -328,7 +336,7 @@ int res_pick_cfg(clp_handle h) {
 
 template <typename T>
 cudaError_t res_set_attrs(clp_handle h, int c, bool sharded) {
-  const int bytes = (int)res_smem_bytes(h, c);
+  const int bytes = (int)res_launch_smem(h, c);
   return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
     if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
     else {
@@ -364,13 +372,15 @@ ResArgs res_args(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
   a.spin_limit = (long long)h->spin_seconds * 1900000000LL;
   a.ring_stages = kResCfgs[h->res_cfg_eff].ring ? kResCfgs[h->res_cfg_eff].D : 0;
+  a.smem_bytes = res_launch_smem(h, h->res_cfg_eff);
+  a.prof_cta = h->prof_ctas ? h->prof_buf.as<double>() : nullptr;
   return a;
 }
 
 template <typename T>
 cudaError_t launch_resident_solver(clp_handle h, ResArgs& a) {
   const int c = h->res_cfg_eff;
-  const size_t bytes = res_smem_bytes(h, c);
+  const size_t bytes = res_launch_smem(h, c);
   void* args[] = {&a};
   return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
     if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
@@ -385,7 +395,7 @@ cudaError_t launch_resident_solver(clp_handle h, ResArgs& a) {
 template <typename T>
 cudaError_t launch_resident_matvec(clp_handle h, const double* v, double d, double* y, double* Mv, double* Cv) {
   const int c = h->res_cfg_eff;
-  const size_t bytes = res_smem_bytes(h, c);
+  const size_t bytes = res_launch_smem(h, c);
   ResArgs a = res_args(h);
   return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
     if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
@@ -790,6 +800,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   cudaError_t le;
   if (h->dense_mode_eff == 6) {
+    if (h->prof_ctas) CLP_CUDA(h, h->prof_buf.ensure((size_t)h->res_G * 4 * sizeof(double)));
     ResArgs ra = res_args(h);
     le = (h->storage == CLP_STORE_F64) ? launch_resident_solver<double>(h, ra) : launch_resident_solver<float>(h, ra);
   } else {
@@ -807,6 +818,17 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
 
   const SolverOut so = *reinterpret_cast<const SolverOut*>(h->pinned);
   h->seq = so.seq_end;
+  if (h->prof_ctas && h->dense_mode_eff == 6) {  // diagnostics: spread of the per-CTA phase times
+    std::vector<double> pc((size_t)h->res_G * 4);
+    CLP_CUDA(h, cudaMemcpy(pc.data(), h->prof_buf.p, pc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const char* nm[3] = {"sweeps", "epilogues", "exchanges"};
+    for (int q = 0; q < 3; ++q) {
+      double lo = 1e300, hi = 0, sum = 0;
+      for (int b = 0; b < h->res_G; ++b) { const double x = pc[(size_t)b * 4 + q]; lo = std::min(lo, x); hi = std::max(hi, x); sum += x; }
+      std::fprintf(stderr, "[clp prof] %-9s per solve: min %.3f  mean %.3f  max %.3f ms over %d CTAs (%lld evaluations)\n", nm[q],
+                   1e-6 * lo, 1e-6 * sum / h->res_G, 1e-6 * hi, h->res_G, (long long)so.n_evals);
+    }
+  }
   if (so.status != 0) {
     h->shard_ready = false;  // sequence numbers may have diverged between ranks
     return fail(h, CLP_ERR_TIMEOUT, "solver kernel: device-wide barrier / peer exchange timed out");
@@ -944,7 +966,7 @@ int clp_destroy(clp_handle h) {
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
   for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->F12, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->sp_part, &h->sp_item, &h->sp_rowid, &h->sp_rank, &h->parts, &h->small,
-                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf, &h->res_vecs, &h->res_cand, &h->res_pieces})
+                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf, &h->res_vecs, &h->res_cand, &h->res_pieces, &h->prof_buf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1366,7 +1388,8 @@ struct clp_batch_s {
   clp_params prm;
   std::string err;
   int sm_count = 0, smem_optin = 0;
-  DevBuf in_d1, in_d2, in_a, in_u0, out_u, probs, outs, nnz, sync, scratch;
+  DevBuf in_d1, in_d2, in_a, in_u0, out_u, probs, outs, nnz, sync, scratch, prof;
+  int prof_on = env_int("CLP_PROF_BATCH", 0);
   void* pinned = nullptr; size_t pinned_cap = 0;
   int last_ctas = 0; long long last_scratch = 0, last_nnz = 0;
 };
@@ -1491,6 +1514,7 @@ int batch_solve(clp_batch b, int kind, int dd, int32_t nprob, const double* cons
   ba.prm.rescale_u0 = P.rescale_u0 ? 1 : 0;
   ba.p0 = p0; ba.p1 = p1; ba.p2 = p2; ba.p3 = p3; ba.affinityeps = P.affinityeps;
   ba.sb = b->sync.as<SyncBlock>(); ba.spin_limit = 4LL * 1900000000LL;
+  if (b->prof_on) { CLP_BCUDA(b, b->prof.ensure((size_t)nprob * 4 * sizeof(unsigned long long))); ba.prof = b->prof.as<unsigned long long>(); }
   CLP_BCUDA(b, cudaEventRecord(b->ev0, b->stream));
   rc = (kind == 1) ? batch_launch<1, 6>(b, ba, grid, bs.total) : (dd == 3 ? batch_launch<0, 3>(b, ba, grid, bs.total) : batch_launch<0, 2>(b, ba, grid, bs.total));
   if (rc) return rc;
@@ -1507,6 +1531,14 @@ int batch_solve(clp_batch b, int kind, int dd, int32_t nprob, const double* cons
   CLP_BCUDA(b, cudaStreamSynchronize(b->stream));
   float ms = 0.f;
   CLP_BCUDA(b, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  if (b->prof_on) {
+    std::vector<unsigned long long> pr((size_t)nprob * 4);
+    CLP_BCUDA(b, cudaMemcpy(pr.data(), b->prof.p, pr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double acc[4] = {0, 0, 0, 0};
+    for (int p = 0; p < nprob; ++p) for (int q = 0; q < 4; ++q) acc[q] += 1e-6 * (double)pr[(size_t)p * 4 + q];
+    std::fprintf(stderr, "[clp batch prof] %d problems (max m %d), %d CTAs, kernel %.3f ms; mean per problem: score %.3f  build %.3f  solve %.3f  total %.3f ms\n",
+                 nprob, max_m, grid, ms, acc[0] / nprob, acc[1] / nprob, acc[2] / nprob, acc[3] / nprob);
+  }
   if (h_sb.error == 2) return bfail(b, CLP_ERR_INVALID, "association index out of range of D1/D2 in a batched problem");
   if (h_sb.error != 0) return bfail(b, CLP_ERR_TIMEOUT, "batch kernel: an in-kernel wait timed out");
   b->last_ctas = grid; b->last_scratch = (long long)grid * (long long)L.total; b->last_nnz = 0;
@@ -1576,7 +1608,7 @@ int clp_batch_create(int device, clp_batch* out) {
 int clp_batch_destroy(clp_batch b) {
   if (!b) return CLP_OK;
   cudaSetDevice(b->device);
-  for (DevBuf* d : {&b->in_d1, &b->in_d2, &b->in_a, &b->in_u0, &b->out_u, &b->probs, &b->outs, &b->nnz, &b->sync, &b->scratch}) d->release();
+  for (DevBuf* d : {&b->in_d1, &b->in_d2, &b->in_a, &b->in_u0, &b->out_u, &b->probs, &b->outs, &b->nnz, &b->sync, &b->scratch, &b->prof}) d->release();
   if (b->pinned) cudaFreeHost(b->pinned);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);

@@ -61,6 +61,8 @@ struct ResArgs {
   unsigned long long seq0;
   long long spin_limit;    // clock64 ticks a wait may last before it raises the time-out flag
   int ring_stages;         // > 0: cp.async.bulk ring with this many stages per warp (RING instances)
+  unsigned int smem_bytes; // dynamic shared memory of the launch (0: just the plan's minimum)
+  double* prof_cta;        // nullable: [G][4] per-CTA phase times in ns (sweeps, epilogues, exchanges) -- diagnostics
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -99,9 +101,13 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned int parity, int* e
 struct ResSmem {
   unsigned int off_red, off_fin, off_wb, off_misc, off_bar, off_ring, total;
   unsigned int stage_bytes;
+  // whatever the launch grants beyond `total` (smem_bytes) holds the CTA's piece table and the per-row solver state
+  // (8 doubles per row) so that the per-row epilogue stays on chip; a CTA whose items / rows exceed the capacities
+  // uses the HBM copies instead
+  unsigned int off_pieces, pieces_cap, off_state, state_cap;
 };
 __host__ __device__ inline unsigned int res_round_bytes(int U, int esize) { return (unsigned int)(32 * U * (4 * esize + 8)); }
-__host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages, int U, int esize) {
+__host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages, int U, int esize, unsigned int smem_bytes = 0) {
   ResSmem s;
   unsigned int o = (unsigned int)(((m + 1 + 1) & ~1) * 8);        // vs[0..m], vs[m] = 0
   s.off_red = o; o += (unsigned int)(NW * kRedVals * 8);
@@ -114,6 +120,14 @@ __host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages,
   s.stage_bytes = res_round_bytes(U, esize);
   s.off_ring = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages : 0) * s.stage_bytes;
   s.total = o;
+  o = (o + 15u) & ~15u;
+  const unsigned int rem = smem_bytes > o + 256u ? smem_bytes - o - 128u : 0u;
+  s.pieces_cap = rem / 4u / (kPieceVals * 8u);
+  if (s.pieces_cap > 512u) s.pieces_cap = 512u;
+  s.off_pieces = o; o += s.pieces_cap * kPieceVals * 8u;
+  s.state_cap = (rem - s.pieces_cap * kPieceVals * 8u) / (R_SLOTS * 8u);
+  if (s.state_cap > 4096u) s.state_cap = 4096u;
+  s.off_state = o;
   return s;
 }
 
@@ -293,7 +307,8 @@ __device__ __forceinline__ unsigned int res_item_of(const unsigned int* itemptr,
 
 // COH: the compact copy was written earlier IN THIS LAUNCH (batched problems): no ld.global.nc, L2-coherent loads instead
 template <typename T, int NT, int U, int D, bool RING, bool COH = false>
-__device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, unsigned char* smem, const ResSmem& plan, int* errp) {
+__device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, unsigned char* smem, const ResSmem& plan, int* errp,
+                          double* ptab, unsigned int isub) {
   constexpr int NW = NT / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SparseView& sp = a.sp;
@@ -306,7 +321,7 @@ __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, uns
   const T* val = reinterpret_cast<const T*>(sp.val);
   const unsigned short* idx = sp.off16;
   const unsigned int padk = (unsigned int)a.m | ((unsigned int)a.m << 16);  // column m holds 0.0
-  double* pieces = a.pieces + ((size_t)bid * NW + warp) * kPieceVals;  // + item * 8
+  double* pieces = ptab + (size_t)warp * kPieceVals;  // + (item - isub) * 8
 
   // ---- producer cursor (warp-uniform): the piece being loaded
   unsigned int cit = res_item_of(itemptr, it0, it1 - 1, s0);
@@ -338,7 +353,7 @@ __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, uns
       accC += __shfl_xor_sync(0xffffffffu, accC, o);
     }
     if (lane < 4) {
-      double* p = pieces + (size_t)item * kPieceVals;
+      double* p = pieces + (size_t)(item - isub) * kPieceVals;
       p[lane] = accM; p[4 + lane] = accC;
     }
     aM[0] = aM[1] = aC[0] = aC[1] = 0.0;
@@ -434,8 +449,8 @@ __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, uns
 
 // sum of the pieces of one row (item it of this CTA, member s) in stream order
 template <int NT>
-__device__ __forceinline__ void res_gather_pieces(const ResArgs& a, const int bid, const unsigned int* wb, unsigned int it, int s,
-                                                  double& Mv, double& Cv) {
+__device__ __forceinline__ void res_gather_pieces(const ResArgs& a, const double* ptab, unsigned int isub, bool ptab_shared,
+                                                  const unsigned int* wb, unsigned int it, int s, double& Mv, double& Cv) {
   constexpr int NW = NT / 32;
   const unsigned int b = a.sp.itemptr[it], e = a.sp.itemptr[it + 1];
   double m_ = 0.0, c_ = 0.0;
@@ -443,10 +458,11 @@ __device__ __forceinline__ void res_gather_pieces(const ResArgs& a, const int bi
     int w0 = 0, w1 = 0;  // warps holding the first and the last chunk of the item: largest w with wb[w] <= chunk
 #pragma unroll 1
     for (int w = 1; w < NW; ++w) { if (wb[w] <= b) w0 = w; if (wb[w] <= e - 1u) w1 = w; }
-    const double* p = a.pieces + ((size_t)bid * NW + w0 + it) * kPieceVals;
+    const double* p = ptab + ((size_t)w0 + (it - isub)) * kPieceVals;
     for (int w = w0; w <= w1; ++w, p += kPieceVals) {
       if (wb[w + 1] <= wb[w]) continue;  // warp without chunks
-      m_ += __ldcg(p + s); c_ += __ldcg(p + 4 + s);
+      if (ptab_shared) { m_ += p[s]; c_ += p[4 + s]; }
+      else { m_ += __ldcg(p + s); c_ += __ldcg(p + 4 + s); }
     }
   }
   Mv = m_; Cv = c_;
@@ -530,7 +546,7 @@ template <typename T, int NT, int U, int D, bool RING, bool SHARDED, bool SOLO, 
 __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   constexpr int NW = NT / 32;
   const int bid = SOLO ? 0 : (int)blockIdx.x;  // CTA index within the problem (batched: one CTA per problem)
-  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T));
+  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T), a.smem_bytes);
   double* vs = reinterpret_cast<double*>(smem);
   double* red_s = reinterpret_cast<double*>(smem + plan.off_red);
   double* fin = reinterpret_cast<double*>(smem + plan.off_fin);
@@ -554,7 +570,17 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   }
   __syncthreads();
 
-  auto V = [&](int slot) -> double* { return a.vecs + (size_t)slot * mp; };
+  // piece table and per-row state (u, gradF, Mhat u, Chat u of the current and the next iterate): on chip when the
+  // CTA's items / rows fit what the launch granted beyond the plan, else in HBM
+  const bool ptab_sh = (it1 - it0) + (unsigned int)NW <= plan.pieces_cap;
+  double* const ptab = ptab_sh ? reinterpret_cast<double*>(smem + plan.off_pieces) : a.pieces + (size_t)bid * NW * kPieceVals;
+  const unsigned int isub = ptab_sh ? it0 : 0u;
+  const bool st_sh = (unsigned int)nrow <= plan.state_cap;
+  double* const st_sm = reinterpret_cast<double*>(smem + plan.off_state);
+  const unsigned int st_cap = plan.state_cap;
+  auto S = [&](int slot, int t_, int i) -> double& {
+    return st_sh ? st_sm[(size_t)slot * st_cap + t_] : a.vecs[(size_t)slot * mp + i];
+  };
   // candidate trial points: parity par, kind 0 = "accept" (max(v + gradFnew, 0)), 1 = "reject" (max(u + alpha beta gradF, 0))
   auto cand_store = [&](int par, int kind, int i, double v, unsigned int tag) {
     const size_t off = (size_t)(par * 2 + kind) * mp + i;
@@ -586,7 +612,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   if (!res_exchange<NT, SHARDED, SOLO>(a, bid, loc, vals, red_par, round, seq, red_s, fin)) { status = 5; goto finish; } \
   RES_LAP(ns_ex);
 #define RES_SWEEP()                                                                                 \
-  res_sweep<T, NT, U, D, RING, COH>(a, bid, vs, smem, plan, errp);                                       \
+  res_sweep<T, NT, U, D, RING, COH>(a, bid, vs, smem, plan, errp, ptab, isub);                                       \
   ++n_matvec;                                                                                       \
   __syncthreads();                                                                                  \
   RES_LAP(ns_mv);
@@ -604,7 +630,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
       double t = a.u0[i];
       if (P.rescale_u0) {
         double Mv, Cv;
-        res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+        res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
         t = __dadd_rn(Mv, t);
       }
       cand_store(cpar ^ 1, 0, i, t, tag);
@@ -626,9 +652,9 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     RES_FOR_ROWS(lr, itx, sx) {
       const int i = a.row0 + lr;
       double Mv, Cv;
-      res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+      res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
       const double ui = vs[i];
-      V(R_U0 + cur)[i] = ui; V(R_MV0 + cur)[i] = Mv; V(R_CV0 + cur)[i] = Cv;
+      S(R_U0 + cur, t_, i) = ui; S(R_MV0 + cur, t_, i) = Mv; S(R_CV0 + cur, t_, i) = Cv;
       const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sumu), Cv), ui);
       if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += __dadd_rn(Mv, ui) / cbu; }
     }
@@ -644,9 +670,9 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
       const unsigned int tag = (unsigned int)(seq + 1);
       RES_FOR_ROWS(lr, itx, sx) {
         const int i = a.row0 + lr;
-        const double ui = V(R_U0 + cur)[i];
-        const double g = grad_entry(ui, sum_cur, V(R_MV0 + cur)[i], V(R_CV0 + cur)[i], d);
-        V(R_G0 + cur)[i] = g;
+        const double ui = S(R_U0 + cur, t_, i);
+        const double g = grad_entry(ui, sum_cur, S(R_MV0 + cur, t_, i), S(R_CV0 + cur, t_, i), d);
+        S(R_G0 + cur, t_, i) = g;
         loc[0] += ui * g;
         double w = __dadd_rn(ui, __dmul_rn(1.0, g)); w = (w < 0.0) ? 0.0 : w;
         loc[1] += w * w;
@@ -675,11 +701,11 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         RES_FOR_ROWS(lr, itx, sx) {
           const int i = a.row0 + lr;
           double Mv, Cv;
-          res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+          res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
           const double un = vs[i];
           const double g = grad_entry(un, sumv, Mv, Cv, d);
-          V(R_U0 + nxt)[i] = un; V(R_G0 + nxt)[i] = g; V(R_MV0 + nxt)[i] = Mv; V(R_CV0 + nxt)[i] = Cv;
-          const double uo = V(R_U0 + cur)[i], go = V(R_G0 + cur)[i];
+          S(R_U0 + nxt, t_, i) = un; S(R_G0 + nxt, t_, i) = g; S(R_MV0 + nxt, t_, i) = Mv; S(R_CV0 + nxt, t_, i) = Cv;
+          const double uo = S(R_U0 + cur, t_, i), go = S(R_G0 + cur, t_, i);
           loc[0] += un * g;
           const double du = __dsub_rn(un, uo);
           loc[1] += du * du;
@@ -712,9 +738,9 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     RES_ZERO();
     RES_FOR_ROWS(lr, itx, sx) {
       const int i = a.row0 + lr;
-      const double ui = V(R_U0 + cur)[i];
-      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), V(R_CV0 + cur)[i]), ui);
-      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(V(R_MV0 + cur)[i], ui) / cbu); }
+      const double ui = S(R_U0 + cur, t_, i);
+      const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), S(R_CV0 + cur, t_, i)), ui);
+      if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(S(R_MV0 + cur, t_, i), ui) / cbu); }
     }
     RES_EXCHANGE();
     if (vals[0] > 0.0) d += vals[1] / vals[0];
@@ -727,7 +753,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     const size_t off = (size_t)4 * mp;
     RES_FOR_ROWS(lr, itx, sx) {
       const int i = a.row0 + lr;
-      const double ui = V(R_U0 + cur)[i];
+      const double ui = S(R_U0 + cur, t_, i);
       ll_store(a.ll + off + i, ui, tag);
       for (int r = 0; r < a.world; ++r)
         if (r != a.rank) ll_store(a.peer_ll[r] + off + i, ui, tag);
@@ -736,10 +762,14 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     RES_EXCHANGE();  // also the last rendez-vous: no rank overwrites a peer's cells while it is still inside this launch
     for (int i = bid * NT + threadIdx.x; i < m; i += a.G * NT) a.u_final[i] = ll_load(a.ll + off + i, tag, errp);
   } else {
-    RES_FOR_ROWS(lr, itx, sx) { const int i = a.row0 + lr; a.u_final[i] = V(R_U0 + cur)[i]; }
+    RES_FOR_ROWS(lr, itx, sx) { const int i = a.row0 + lr; a.u_final[i] = S(R_U0 + cur, t_, i); }
   }
 
 finish:
+  if (a.prof_cta && threadIdx.x == 0) {
+    a.prof_cta[(size_t)bid * 4 + 0] = (double)ns_mv; a.prof_cta[(size_t)bid * 4 + 1] = (double)ns_cb;
+    a.prof_cta[(size_t)bid * 4 + 2] = (double)ns_ex; a.prof_cta[(size_t)bid * 4 + 3] = (double)(it1 - it0);
+  }
   if (bid == 0 && threadIdx.x == 0) {
     if (*reinterpret_cast<volatile int*>(errp) != 0) status = 5;
     a.out->F = F; a.out->d = d; a.out->ifinal = i_outer; a.out->cur = cur; a.out->status = status;
@@ -766,7 +796,7 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
   extern __shared__ __align__(128) unsigned char clp_res_smem[];
   unsigned char* smem = clp_res_smem;
   constexpr int NW = NT / 32;
-  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T));
+  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T), a.smem_bytes);
   double* vs = reinterpret_cast<double*>(smem);
   double* red_s = reinterpret_cast<double*>(smem + plan.off_red);
   double* fin = reinterpret_cast<double*>(smem + plan.off_fin);
@@ -781,7 +811,10 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
   }
   __syncthreads();
   const double sumv = res_stage<NT, false>(RS_RAW, a.m, v, nullptr, 0u, 1.0, vs, red_s, fin, &a.sb->error, a.spin_limit);
-  res_sweep<T, NT, U, D, RING>(a, bid, vs, smem, plan, &a.sb->error);
+  const bool ptab_sh = (it1 - it0) + (unsigned int)NW <= plan.pieces_cap;
+  double* const ptab = ptab_sh ? reinterpret_cast<double*>(smem + plan.off_pieces) : a.pieces + (size_t)bid * NW * kPieceVals;
+  const unsigned int isub = ptab_sh ? it0 : 0u;
+  res_sweep<T, NT, U, D, RING>(a, bid, vs, smem, plan, &a.sb->error, ptab, isub);
   __syncthreads();
   const int nrow = (int)(it1 - it0) * 4;
   for (int t = threadIdx.x; t < nrow; t += NT) {
@@ -790,7 +823,7 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
     const int lr = (int)a.sp.rowid[4u * itx + sx];
     if (lr >= a.rows) continue;
     double Mv, Cv;
-    res_gather_pieces<NT>(a, bid, wb, itx, sx, Mv, Cv);
+    res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
     const int i = a.row0 + lr;
     if (Mv_out) Mv_out[i] = Mv;
     if (Cv_out) Cv_out[i] = Cv;

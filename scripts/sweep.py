@@ -5,7 +5,7 @@
         matrix fits the 126 MB L2 are reported but flagged (they are not HBM measurements).
   * c1 (m=1000, Bunny-like, rho=.9) and c3 (PointNormalDistance m=10000): score + solve timings, density,
         evaluation counts, inlier precision/recall, and the CPU oracle beside them.
-Writes one JSON object per line to gpurun_out/sweep_r01.jsonl and prints them."""
+Writes one JSON object per line to gpurun_out/sweep_r02.jsonl and prints them."""
 import ctypes as C
 import json
 import os
@@ -21,7 +21,7 @@ import clipper_b200 as clp  # noqa: E402
 from clipper_b200 import _capi, datagen  # noqa: E402
 from bench import measured_peaks, oracle_step, cpu_cores  # noqa: E402
 
-out_path = os.path.join(ROOT, "gpurun_out", "sweep_r01.jsonl")
+out_path = os.path.join(ROOT, "gpurun_out", "sweep_r02.jsonl")
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
 fout = open(out_path, "w")
 peak, _ = measured_peaks()
@@ -42,6 +42,7 @@ def matvec_sweep():
             prob = datagen.config_problem("c2", m); cfg = prob["cfg"]
             ip = clp.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = cfg["sigma"], cfg["epsilon"]
             c = clp.CLIPPER(clp.invariants.EuclideanDistance(ip), clp.Params(), storage=storage)
+            c.set_dense_mode(0)  # config 5 is the DENSE Md.v sweep: full matrix, 4 m^2 (8 m^2) bytes per pass
             t0 = time.perf_counter()
             c.score_pairwise_consistency(prob["D1"], prob["D2"], prob["A"])
             t_score = time.perf_counter() - t0
@@ -51,9 +52,19 @@ def matvec_sweep():
             _capi.check(c.handle, L.clp_matvec_dev(c.handle, v.data_ptr(), 1.0, y.data_ptr(), None, None, 50, C.byref(ms)))
             byts = esz * m * m + 16 * m
             gbs = byts / (ms.value * 1e-3) / 1e9
-            emit({"config": "c5", "storage": "f32" if storage == 0 else "f64", "m": m, "ms_per_matvec": ms.value,
-                  "algorithmic_GB": byts / 1e9, "GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak,
-                  "l2_resident": bool(esz * m * m < 126e6), "t_score_call_s": t_score})
+            rec = {"config": "c5", "storage": "f32" if storage == 0 else "f64", "m": m, "ms_per_matvec": ms.value,
+                   "algorithmic_GB": byts / 1e9, "GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak,
+                   "l2_resident": bool(esz * m * m < 126e6), "t_score_call_s": t_score}
+            # the compact copy the solver actually sweeps (auto: resident full rows for m <= 27648, else column segments)
+            c.set_dense_mode(4)
+            mode = c.dense_mode()
+            if mode in (3, 6):
+                _capi.check(c.handle, L.clp_matvec_dev(c.handle, v.data_ptr(), 1.0, y.data_ptr(), None, None, 5, C.byref(ms)))
+                _capi.check(c.handle, L.clp_matvec_dev(c.handle, v.data_ptr(), 1.0, y.data_ptr(), None, None, 50, C.byref(ms)))
+                kept, pb = c.sparse_info()
+                rec.update(compact_mode=mode, compact_ms=ms.value, compact_bytes=pb, compact_GBps=pb / ms.value / 1e6,
+                           compact_frac=pb / ms.value / 1e6 / peak, compact_l2_resident=bool(pb < 126e6))
+            emit(rec)
             del c
             torch.cuda.empty_cache()
 
