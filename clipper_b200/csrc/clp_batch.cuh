@@ -344,13 +344,12 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
       a.ll = nullptr;
       a.mpad = (long long)ld;
       a.pieces = reinterpret_cast<double*>(sc + L.pieces);
-      a.red = nullptr;
       a.sb = ba.sb;
       a.u_final = ba.u_out + P.u_off;
       a.out = ba.out + p;
       a.rank = 0; a.world = 1;
       for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = nullptr; a.peer_comm[r] = nullptr; }
-      a.comm = nullptr; a.seq0 = 0; a.spin_limit = ba.spin_limit; a.ring_stages = 0; a.smem_bytes = 0u; a.prof_cta = nullptr;
+      a.comm = nullptr; a.seq0 = 0; a.spin_limit = ba.spin_limit; a.ring_stages = 0; a.pieces_cap = 0u; a.state_cap = 0u; a.redll = nullptr; a.prof_cta = nullptr;
       sa = a;
     }
     __syncthreads();

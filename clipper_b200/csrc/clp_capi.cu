@@ -115,7 +115,7 @@ struct clp_handle_s {
   DevBuf u0dev;   // [mpad]
   DevBuf ybuf;    // matvec scratch: v | y | Mv | Cv  (4 x mpad)
   DevBuf sync;    // counter (u64) | error (int) | flags (int) | counts (2 x u64)
-  DevBuf res_vecs, res_cand, res_pieces;  // resident solver: R_SLOTS plain vectors | candidate points | piece table
+  DevBuf res_vecs, res_cand, res_pieces, res_redll;  // resident solver: plain vectors | candidate points | piece table | LL sums
   DevBuf panel;   // staging panels for get/set dense
   DevBuf cscbuf;
   void* pinned = nullptr;
@@ -312,10 +312,28 @@ unsigned int res_smem_bytes(clp_handle h, int c) {  // the plan's minimum
   const ResCfg& k = kResCfgs[c];
   return res_smem_plan((int)h->m, k.NT / 32, k.ring ? k.D : 0, k.U, (int)h->esize()).total;
 }
-// what the resident kernels are launched with: everything an SM offers (one CTA per SM anyway); the part beyond the
-// plan's minimum keeps the CTA's piece table and per-row solver state on chip
+// On-chip tables behind the plan's minimum: the CTA's piece table and per-row solver state, sized for 1.5x the mean
+// CTA (a CTA that exceeds them falls back to the HBM copies on its own).  Kept to a few KB on purpose: launching with
+// all 227 KB leaves no L1 and slowed the streaming sweep by 25 % (profiles/r02c_*: 9.8 -> 11.8 ms at config 2).
+void res_pick_caps(clp_handle h, int c, unsigned int* pieces_cap, unsigned int* state_cap) {
+  *pieces_cap = 0; *state_cap = 0;
+  if (!h->res_smem_extra || h->res_G < 1) return;
+  const ResCfg& k = kResCfgs[c];
+  const unsigned int items = (unsigned int)((h->res_NI + h->res_G - 1) / h->res_G);
+  unsigned int pc = items + items / 2 + 4 + (unsigned int)(k.NT / 32), sc = 4 * (items + items / 2 + 4);
+  const unsigned int base = res_smem_plan((int)h->m, k.NT / 32, k.ring ? k.D : 0, k.U, (int)h->esize()).total;
+  const unsigned int budget = std::min<unsigned int>(24u << 10, (unsigned int)std::max(0, h->smem_optin - (int)base - 256));
+  if (pc * 64u + sc * 72u > budget) {  // keep the piece table first, then as much row state as fits -- or none
+    if (pc * 64u > budget) return;
+    sc = 0;
+  }
+  *pieces_cap = pc; *state_cap = sc;
+}
 unsigned int res_launch_smem(clp_handle h, int c) {
-  return std::max(res_smem_bytes(h, c), (unsigned int)std::max(0, h->res_smem_extra ? h->smem_optin : 0));
+  const ResCfg& k = kResCfgs[c];
+  unsigned int pc, sc;
+  res_pick_caps(h, c, &pc, &sc);
+  return res_smem_plan((int)h->m, k.NT / 32, k.ring ? k.D : 0, k.U, (int)h->esize(), pc, sc).total_ext;
 }
 
 // can the resident solver take a problem of this size on this handle?
@@ -363,7 +381,6 @@ ResArgs res_args(clp_handle h) {
   a.ll = h->llbuf.as<uint4>();
   a.mpad = h->mpad;
   a.pieces = h->res_pieces.as<double>();
-  a.red = h->small.as<double>() + kMaxSeg;
   a.sb = h->sync.as<SyncBlock>();
   a.u_final = reinterpret_cast<double*>(reinterpret_cast<char*>(h->result.p) + 256);
   a.out = reinterpret_cast<SolverOut*>(h->result.p);
@@ -372,7 +389,8 @@ ResArgs res_args(clp_handle h) {
   for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
   a.spin_limit = (long long)h->spin_seconds * 1900000000LL;
   a.ring_stages = kResCfgs[h->res_cfg_eff].ring ? kResCfgs[h->res_cfg_eff].D : 0;
-  a.smem_bytes = res_launch_smem(h, h->res_cfg_eff);
+  res_pick_caps(h, h->res_cfg_eff, &a.pieces_cap, &a.state_cap);
+  a.redll = h->res_redll.as<uint4>();
   a.prof_cta = h->prof_ctas ? h->prof_buf.as<double>() : nullptr;
   return a;
 }
@@ -492,7 +510,7 @@ int build_sparse(clp_handle h, bool force, bool resident) {
     CLP_CUDA(h, h->res_vecs.ensure((size_t)R_SLOTS * h->mpad * sizeof(double)));
     CLP_CUDA(h, h->res_cand.ensure((size_t)4 * h->mpad * sizeof(double)));
     CLP_CUDA(h, h->res_pieces.ensure(((size_t)NI + (size_t)G * NW + 8) * kPieceVals * sizeof(double)));
-    CLP_CUDA(h, h->small.ensure(((size_t)kMaxSeg + (size_t)2 * std::max(G, h->plan.G) * kRedVals) * sizeof(double)));
+    CLP_CUDA(h, h->res_redll.ensure((size_t)2 * G * kRedVals * sizeof(uint4)));
   }
   CLP_CUDA(h, h->sp_part.ensure(2 * ((size_t)G + 1) * sizeof(unsigned int)));
   sparse_partition_kernel<<<(G + 1 + 255) / 256, 256, 0, h->stream>>>(h->sp.itemptr, h->rows_pad, nseg, G, h->sp_part.as<unsigned int>(),
@@ -801,6 +819,8 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   cudaError_t le;
   if (h->dense_mode_eff == 6) {
     if (h->prof_ctas) CLP_CUDA(h, h->prof_buf.ensure((size_t)h->res_G * 4 * sizeof(double)));
+    // the per-CTA partial sums travel as LL cells tagged with the launch-local round number: start from tag 0
+    CLP_CUDA(h, cudaMemsetAsync(h->res_redll.p, 0, (size_t)2 * h->res_G * kRedVals * sizeof(uint4), h->stream));
     ResArgs ra = res_args(h);
     le = (h->storage == CLP_STORE_F64) ? launch_resident_solver<double>(h, ra) : launch_resident_solver<float>(h, ra);
   } else {
@@ -966,7 +986,7 @@ int clp_destroy(clp_handle h) {
     if (h->peer_opened[r]) { cudaIpcCloseMemHandle(h->peer_open_ptr[r][0]); cudaIpcCloseMemHandle(h->peer_open_ptr[r][1]); }
   h->comm.release();
   for (DevBuf* b : {&h->Mbuf, &h->A_dev, &h->E1, &h->E2, &h->F12, &h->D1dev, &h->D2dev, &h->vecs, &h->llbuf, &h->d2buf, &h->plan2buf, &h->sp_val, &h->sp_col, &h->sp_ptr4, &h->sp_part, &h->sp_item, &h->sp_rowid, &h->sp_rank, &h->parts, &h->small,
-                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf, &h->res_vecs, &h->res_cand, &h->res_pieces, &h->prof_buf})
+                    &h->result, &h->u0dev, &h->ybuf, &h->sync, &h->panel, &h->cscbuf, &h->res_vecs, &h->res_cand, &h->res_pieces, &h->res_redll, &h->prof_buf})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -50,7 +50,6 @@ struct ResArgs {
   uint4* ll;               // world  > 1: the same as LL cells + one more vector (final iterate): [5][mpad], replicated
   long long mpad;
   double* pieces;          // [(NI + G * warps)][8]
-  double* red;             // [2][G][8] per-CTA partial sums
   SyncBlock* sb;
   double* u_final;         // [m]
   SolverOut* out;
@@ -61,7 +60,8 @@ struct ResArgs {
   unsigned long long seq0;
   long long spin_limit;    // clock64 ticks a wait may last before it raises the time-out flag
   int ring_stages;         // > 0: cp.async.bulk ring with this many stages per warp (RING instances)
-  unsigned int smem_bytes; // dynamic shared memory of the launch (0: just the plan's minimum)
+  unsigned int pieces_cap, state_cap;  // on-chip piece table (entries) / row state (rows) per CTA, 0: keep them in HBM
+  uint4* redll;            // [2][G][8] per-CTA partial sums as self-validating LL cells (zeroed before the launch)
   double* prof_cta;        // nullable: [G][4] per-CTA phase times in ns (sweeps, epilogues, exchanges) -- diagnostics
 };
 
@@ -101,13 +101,15 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned int parity, int* e
 struct ResSmem {
   unsigned int off_red, off_fin, off_wb, off_misc, off_bar, off_ring, total;
   unsigned int stage_bytes;
-  // whatever the launch grants beyond `total` (smem_bytes) holds the CTA's piece table and the per-row solver state
-  // (8 doubles per row) so that the per-row epilogue stays on chip; a CTA whose items / rows exceed the capacities
-  // uses the HBM copies instead
-  unsigned int off_pieces, pieces_cap, off_state, state_cap;
+  // optional on-chip tables behind the plan's minimum (capacities chosen by the host, a few KB: the more shared
+  // memory a CTA takes, the less L1 is left for the streaming loads): the CTA's piece table, and per row the solver
+  // state (8 doubles) and a descriptor (global row, first / last warp of its pieces).  A CTA whose items / rows
+  // exceed the capacities uses the HBM copies instead.
+  unsigned int off_pieces, pieces_cap, off_state, state_cap, off_desc, total_ext;
 };
 __host__ __device__ inline unsigned int res_round_bytes(int U, int esize) { return (unsigned int)(32 * U * (4 * esize + 8)); }
-__host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages, int U, int esize, unsigned int smem_bytes = 0) {
+__host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages, int U, int esize, unsigned int pieces_cap = 0,
+                                                 unsigned int state_cap = 0) {
   ResSmem s;
   unsigned int o = (unsigned int)(((m + 1 + 1) & ~1) * 8);        // vs[0..m], vs[m] = 0
   s.off_red = o; o += (unsigned int)(NW * kRedVals * 8);
@@ -121,13 +123,11 @@ __host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages,
   s.off_ring = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages : 0) * s.stage_bytes;
   s.total = o;
   o = (o + 15u) & ~15u;
-  const unsigned int rem = smem_bytes > o + 256u ? smem_bytes - o - 128u : 0u;
-  s.pieces_cap = rem / 4u / (kPieceVals * 8u);
-  if (s.pieces_cap > 512u) s.pieces_cap = 512u;
-  s.off_pieces = o; o += s.pieces_cap * kPieceVals * 8u;
-  s.state_cap = (rem - s.pieces_cap * kPieceVals * 8u) / (R_SLOTS * 8u);
-  if (s.state_cap > 4096u) s.state_cap = 4096u;
-  s.off_state = o;
+  s.pieces_cap = pieces_cap; s.state_cap = state_cap;
+  s.off_pieces = o; o += pieces_cap * kPieceVals * 8u;
+  s.off_state = o; o += state_cap * R_SLOTS * 8u;
+  s.off_desc = o; o += state_cap * 8u;
+  s.total_ext = o;
   return s;
 }
 
@@ -181,27 +181,6 @@ __device__ __forceinline__ void res_publish(const double (&loc)[kRedVals], doubl
     for (int w = 0; w < NT / 32; ++w) s += red_s[w * kRedVals + threadIdx.x];
     red_row[threadIdx.x] = s;
   }
-}
-
-// every CTA adds the G rows of the table in the same order: thread (q = t & 7, c = t >> 3) walks rows c, c + NT/8, ...;
-// the NT/8 partial groups are then added warp by warp.  Result in fin[0..7] (shared), visible to all threads.
-template <int NT>
-__device__ __forceinline__ void res_reduce_table(const double* table, int G, double* red_s, double* fin) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = threadIdx.x & 7;
-  double s = 0.0;
-  for (int c = threadIdx.x >> 3; c < G; c += NT / 8) s += __ldcg(table + (size_t)c * kRedVals + q);
-  s += __shfl_xor_sync(0xffffffffu, s, 8);
-  s += __shfl_xor_sync(0xffffffffu, s, 16);
-  __syncthreads();
-  if (lane < kRedVals) red_s[warp * kRedVals + lane] = s;
-  __syncthreads();
-  if (threadIdx.x < kRedVals) {
-    double t = 0.0;
-    for (int w = 0; w < NT / 32; ++w) t += red_s[w * kRedVals + threadIdx.x];
-    fin[threadIdx.x] = t;
-  }
-  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -447,23 +426,28 @@ __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, uns
   }
 }
 
-// sum of the pieces of one row (item it of this CTA, member s) in stream order
+// warps holding the first and the last chunk of item it (w0 > w1: the item is empty)
 template <int NT>
-__device__ __forceinline__ void res_gather_pieces(const ResArgs& a, const double* ptab, unsigned int isub, bool ptab_shared,
-                                                  const unsigned int* wb, unsigned int it, int s, double& Mv, double& Cv) {
+__device__ __forceinline__ void res_piece_range(const ResArgs& a, const unsigned int* wb, unsigned int it, int& w0, int& w1) {
   constexpr int NW = NT / 32;
   const unsigned int b = a.sp.itemptr[it], e = a.sp.itemptr[it + 1];
-  double m_ = 0.0, c_ = 0.0;
+  w0 = 1; w1 = 0;
   if (e > b) {
-    int w0 = 0, w1 = 0;  // warps holding the first and the last chunk of the item: largest w with wb[w] <= chunk
+    w0 = 0;  // largest w with wb[w] <= chunk
 #pragma unroll 1
     for (int w = 1; w < NW; ++w) { if (wb[w] <= b) w0 = w; if (wb[w] <= e - 1u) w1 = w; }
-    const double* p = ptab + ((size_t)w0 + (it - isub)) * kPieceVals;
-    for (int w = w0; w <= w1; ++w, p += kPieceVals) {
-      if (wb[w + 1] <= wb[w]) continue;  // warp without chunks
-      if (ptab_shared) { m_ += p[s]; c_ += p[4 + s]; }
-      else { m_ += __ldcg(p + s); c_ += __ldcg(p + 4 + s); }
-    }
+  }
+}
+
+// sum of the pieces of one row (item it of this CTA, member s) in stream order; wmask: warps that own chunks
+__device__ __forceinline__ void res_gather_pieces(const double* ptab, unsigned int isub, bool ptab_shared, unsigned int wmask,
+                                                  unsigned int it, int s, int w0, int w1, double& Mv, double& Cv) {
+  double m_ = 0.0, c_ = 0.0;
+  const double* p = ptab + ((size_t)w0 + (it - isub)) * kPieceVals;
+  for (int w = w0; w <= w1; ++w, p += kPieceVals) {
+    if (!((wmask >> w) & 1u)) continue;  // warp without chunks
+    if (ptab_shared) { m_ += p[s]; c_ += p[4 + s]; }
+    else { m_ += __ldcg(p + s); c_ += __ldcg(p + 4 + s); }
   }
   Mv = m_; Cv = c_;
 }
@@ -484,22 +468,72 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
     __syncthreads();
     return true;
   } else {
+    // Every CTA publishes its 8 partial sums as self-validating LL cells {lo, tag, hi, tag} and bumps an arrival
+    // counter with a RELAXED atomic: no __threadfence anywhere (a membar.gpu costs about a microsecond, and the
+    // cooperative-groups style barrier needs two).  The counter only tells the waiters when polling is likely to
+    // succeed; correctness comes from the tags: every CTA then reads the whole table, re-polling any cell whose
+    // tag is not this round's, and adds the rows in the same fixed order.
     const int G = a.G;
-    double* table = a.red + (size_t)red_par * G * kRedVals;
-    res_publish<NT>(loc, table + (size_t)bid * kRedVals, red_s);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&a.sb->root[0], 1ULL);
-      const unsigned long long target = round * (unsigned long long)G;
-      const long long t0 = clock64();
-      while (ld_acquire_u64(&a.sb->root[0]) < target) {
-        if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
+    uint4* table = a.redll + (size_t)red_par * G * kRedVals;
+    const unsigned int rtag = (unsigned int)round;
+    {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      double t[kRedVals];
+#pragma unroll
+      for (int q = 0; q < kRedVals; ++q) t[q] = warp_sum(loc[q]);
+      __syncthreads();
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kRedVals; ++q) red_s[warp * kRedVals + q] = t[q];
       }
-      __threadfence();
+      __syncthreads();
+      if (threadIdx.x < kRedVals) {
+        double sacc = 0.0;
+        for (int w = 0; w < NT / 32; ++w) sacc += red_s[w * kRedVals + threadIdx.x];
+        ll_store(table + (size_t)bid * kRedVals + threadIdx.x, sacc, rtag);
+      }
+      if (warp == 0) {
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(&a.sb->root[0]), "l"(1ULL) : "memory");
+          const unsigned long long target = round * (unsigned long long)G;
+          const long long t0 = clock64();
+          unsigned long long seen;
+          do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&a.sb->root[0]) : "memory");
+            if (seen >= target) break;
+          } while (clock64() - t0 <= a.spin_limit);
+          if (seen < target) atomicExch(errp, 1);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    res_reduce_table<NT>(table, G, red_s, fin);
+    {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int q = threadIdx.x & 7;
+      double sacc = 0.0;
+      for (int c = threadIdx.x >> 3; c < G; c += NT / 8) {
+        const uint4* p = table + (size_t)c * kRedVals + q;
+        unsigned lo, t1, hi, t2; long long t0 = 0;
+        for (;;) {
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+          if (t1 == rtag && t2 == rtag) break;
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
+        }
+        sacc += __hiloint2double((int)hi, (int)lo);
+      }
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+      if (lane < kRedVals) red_s[warp * kRedVals + lane] = sacc;
+      __syncthreads();
+      if (threadIdx.x < kRedVals) {
+        double tt = 0.0;
+        for (int w = 0; w < NT / 32; ++w) tt += red_s[w * kRedVals + threadIdx.x];
+        fin[threadIdx.x] = tt;
+      }
+      __syncthreads();
+    }
     if constexpr (SHARDED) {
       const unsigned int tag = (unsigned int)seq;
       const int t = threadIdx.x;
@@ -546,7 +580,7 @@ template <typename T, int NT, int U, int D, bool RING, bool SHARDED, bool SOLO, 
 __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   constexpr int NW = NT / 32;
   const int bid = SOLO ? 0 : (int)blockIdx.x;  // CTA index within the problem (batched: one CTA per problem)
-  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T), a.smem_bytes);
+  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T), a.pieces_cap, a.state_cap);
   double* vs = reinterpret_cast<double*>(smem);
   double* red_s = reinterpret_cast<double*>(smem + plan.off_red);
   double* fin = reinterpret_cast<double*>(smem + plan.off_fin);
@@ -581,6 +615,37 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   auto S = [&](int slot, int t_, int i) -> double& {
     return st_sh ? st_sm[(size_t)slot * st_cap + t_] : a.vecs[(size_t)slot * mp + i];
   };
+  // per-row descriptors (global row, member, piece range): invariant over the solve, kept on chip with the state
+  struct RowDesc { int i; unsigned char s, w0, w1, pad; };
+  RowDesc* const desc = reinterpret_cast<RowDesc*>(smem + plan.off_desc);
+  unsigned int wmask = 0u;
+#pragma unroll 1
+  for (int w = 0; w < NW; ++w) wmask |= (wb[w + 1] > wb[w] ? 1u : 0u) << w;
+  auto row_of = [&](int t_, int& i, unsigned int& itx, int& sx, int& w0, int& w1) -> bool {
+    itx = it0 + (unsigned int)(t_ >> 2);
+    if (st_sh) {
+      const RowDesc dsc = desc[t_];
+      i = dsc.i; sx = dsc.s; w0 = dsc.w0; w1 = dsc.w1;
+      return i >= 0;
+    }
+    sx = t_ & 3;
+    const int lr = (int)a.sp.rowid[4u * itx + sx];
+    i = a.row0 + lr;
+    res_piece_range<NT>(a, wb, itx, w0, w1);
+    return lr < a.rows;
+  };
+  if (st_sh) {
+    for (int t_ = threadIdx.x; t_ < nrow; t_ += NT) {
+      const unsigned int itx = it0 + (unsigned int)(t_ >> 2);
+      const int sx = t_ & 3;
+      const int lr = (int)a.sp.rowid[4u * itx + sx];
+      int w0, w1;
+      res_piece_range<NT>(a, wb, itx, w0, w1);
+      RowDesc dsc; dsc.i = lr < a.rows ? a.row0 + lr : -1; dsc.s = (unsigned char)sx; dsc.w0 = (unsigned char)w0; dsc.w1 = (unsigned char)w1; dsc.pad = 0;
+      desc[t_] = dsc;
+    }
+    __syncthreads();
+  }
   // candidate trial points: parity par, kind 0 = "accept" (max(v + gradFnew, 0)), 1 = "reject" (max(u + alpha beta gradF, 0))
   auto cand_store = [&](int par, int kind, int i, double v, unsigned int tag) {
     const size_t off = (size_t)(par * 2 + kind) * mp + i;
@@ -602,11 +667,9 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, tmark = global_ns();
 #define RES_LAP(acc) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; }
 #define RES_ZERO() _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
-#define RES_FOR_ROWS(lr, itx, sx)                                                                   \
-  for (int t_ = threadIdx.x; t_ < nrow; t_ += NT)                                                   \
-    if (const unsigned int itx = it0 + (unsigned int)(t_ >> 2); true)                               \
-      if (const int sx = t_ & 3; true)                                                              \
-        if (const int lr = (int)a.sp.rowid[4u * itx + sx]; lr < a.rows)
+#define RES_FOR_ROWS(i, itx, sx)                                                                    \
+  for (int t_ = threadIdx.x, i = 0, sx = 0, w0_ = 0, w1_ = 0; t_ < nrow; t_ += NT)                  \
+    if (unsigned int itx = 0u; row_of(t_, i, itx, sx, w0_, w1_))
 #define RES_EXCHANGE()                                                                              \
   RES_LAP(ns_cb);                                                                                   \
   if (!res_exchange<NT, SHARDED, SOLO>(a, bid, loc, vals, red_par, round, seq, red_s, fin)) { status = 5; goto finish; } \
@@ -625,12 +688,11 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     }
     RES_ZERO();
     const unsigned int tag = (unsigned int)(seq + 1);
-    RES_FOR_ROWS(lr, itx, sx) {
-      const int i = a.row0 + lr;
+    RES_FOR_ROWS(i, itx, sx) {
       double t = a.u0[i];
       if (P.rescale_u0) {
         double Mv, Cv;
-        res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
+        res_gather_pieces(ptab, isub, ptab_sh, wmask, itx, sx, w0_, w1_, Mv, Cv);
         t = __dadd_rn(Mv, t);
       }
       cand_store(cpar ^ 1, 0, i, t, tag);
@@ -649,10 +711,9 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     cur = 1;
     sum_cur = sumu;
     RES_ZERO();
-    RES_FOR_ROWS(lr, itx, sx) {
-      const int i = a.row0 + lr;
+    RES_FOR_ROWS(i, itx, sx) {
       double Mv, Cv;
-      res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
+      res_gather_pieces(ptab, isub, ptab_sh, wmask, itx, sx, w0_, w1_, Mv, Cv);
       const double ui = vs[i];
       S(R_U0 + cur, t_, i) = ui; S(R_MV0 + cur, t_, i) = Mv; S(R_CV0 + cur, t_, i) = Cv;
       const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sumu), Cv), ui);
@@ -668,8 +729,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     {
       RES_ZERO();
       const unsigned int tag = (unsigned int)(seq + 1);
-      RES_FOR_ROWS(lr, itx, sx) {
-        const int i = a.row0 + lr;
+      RES_FOR_ROWS(i, itx, sx) {
         const double ui = S(R_U0 + cur, t_, i);
         const double g = grad_entry(ui, sum_cur, S(R_MV0 + cur, t_, i), S(R_CV0 + cur, t_, i), d);
         S(R_G0 + cur, t_, i) = g;
@@ -698,10 +758,9 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         const double alpha_rej = __dmul_rn(alpha, P.beta);
         RES_ZERO();
         const unsigned int tag = (unsigned int)(seq + 1);
-        RES_FOR_ROWS(lr, itx, sx) {
-          const int i = a.row0 + lr;
+        RES_FOR_ROWS(i, itx, sx) {
           double Mv, Cv;
-          res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
+          res_gather_pieces(ptab, isub, ptab_sh, wmask, itx, sx, w0_, w1_, Mv, Cv);
           const double un = vs[i];
           const double g = grad_entry(un, sumv, Mv, Cv, d);
           S(R_U0 + nxt, t_, i) = un; S(R_G0 + nxt, t_, i) = g; S(R_MV0 + nxt, t_, i) = Mv; S(R_CV0 + nxt, t_, i) = Cv;
@@ -736,8 +795,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     }
     // penalty ramp (clipper.cpp:268-280)
     RES_ZERO();
-    RES_FOR_ROWS(lr, itx, sx) {
-      const int i = a.row0 + lr;
+    RES_FOR_ROWS(i, itx, sx) {
       const double ui = S(R_U0 + cur, t_, i);
       const double cbu = __dsub_rn(__dsub_rn(__dmul_rn(1.0, sum_cur), S(R_CV0 + cur, t_, i)), ui);
       if (cbu > P.eps && ui > P.eps) { loc[0] += 1.0; loc[1] += fabs(__dadd_rn(S(R_MV0 + cur, t_, i), ui) / cbu); }
@@ -751,8 +809,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   if constexpr (SHARDED) {
     const unsigned int tag = (unsigned int)(seq + 1);
     const size_t off = (size_t)4 * mp;
-    RES_FOR_ROWS(lr, itx, sx) {
-      const int i = a.row0 + lr;
+    RES_FOR_ROWS(i, itx, sx) {
       const double ui = S(R_U0 + cur, t_, i);
       ll_store(a.ll + off + i, ui, tag);
       for (int r = 0; r < a.world; ++r)
@@ -762,7 +819,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     RES_EXCHANGE();  // also the last rendez-vous: no rank overwrites a peer's cells while it is still inside this launch
     for (int i = bid * NT + threadIdx.x; i < m; i += a.G * NT) a.u_final[i] = ll_load(a.ll + off + i, tag, errp);
   } else {
-    RES_FOR_ROWS(lr, itx, sx) { const int i = a.row0 + lr; a.u_final[i] = S(R_U0 + cur, t_, i); }
+    RES_FOR_ROWS(i, itx, sx) { a.u_final[i] = S(R_U0 + cur, t_, i); }
   }
 
 finish:
@@ -796,7 +853,7 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
   extern __shared__ __align__(128) unsigned char clp_res_smem[];
   unsigned char* smem = clp_res_smem;
   constexpr int NW = NT / 32;
-  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T), a.smem_bytes);
+  const ResSmem plan = res_smem_plan(a.m, NW, RING ? D : 0, U, (int)sizeof(T), a.pieces_cap, a.state_cap);
   double* vs = reinterpret_cast<double*>(smem);
   double* red_s = reinterpret_cast<double*>(smem + plan.off_red);
   double* fin = reinterpret_cast<double*>(smem + plan.off_fin);
@@ -817,13 +874,18 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
   res_sweep<T, NT, U, D, RING>(a, bid, vs, smem, plan, &a.sb->error, ptab, isub);
   __syncthreads();
   const int nrow = (int)(it1 - it0) * 4;
+  unsigned int wmask = 0u;
+#pragma unroll 1
+  for (int w = 0; w < NW; ++w) wmask |= (wb[w + 1] > wb[w] ? 1u : 0u) << w;
   for (int t = threadIdx.x; t < nrow; t += NT) {
     const unsigned int itx = it0 + (unsigned int)(t >> 2);
     const int sx = t & 3;
     const int lr = (int)a.sp.rowid[4u * itx + sx];
     if (lr >= a.rows) continue;
     double Mv, Cv;
-    res_gather_pieces<NT>(a, ptab, isub, ptab_sh, wb, itx, sx, Mv, Cv);
+    int w0_, w1_;
+    res_piece_range<NT>(a, wb, itx, w0_, w1_);
+    res_gather_pieces(ptab, isub, ptab_sh, wmask, itx, sx, w0_, w1_, Mv, Cv);
     const int i = a.row0 + lr;
     if (Mv_out) Mv_out[i] = Mv;
     if (Cv_out) Cv_out[i] = Cv;

@@ -46,8 +46,8 @@ def interleave_permutation(m, world):
     Row-count shards are not byte-balanced when dense rows cluster -- the benchmark generator puts the inlier
     associations last (reference bm_utils.cpp:312-315,344): 1.144x the mean bytes on the last of 8 shards at
     BASELINE config 2.  Scoring the permuted association list permutes M symmetrically; the solution of the
-    permuted problem maps back with unpermute_solution().  Host-side only; opt-in (CLP_SHARD_INTERLEAVE=1 in
-    bench.py --gpus N), not yet measured on hardware."""
+    permuted problem maps back with unpermute_solution().  Host-side only; the default of ShardedCLIPPER's host-pointer
+    scoring (balance=True) and of bench.py --gpus N (CLP_SHARD_INTERLEAVE=0 turns it off)."""
     bounds = [shard_rows(m, r, world) for r in range(world)]
     # slot k of a shard with n rows is due at time (k + 0.5) / n: taking all slots in time order fills every shard
     # at a rate proportional to its size, so any run of consecutive associations is spread evenly
@@ -109,12 +109,23 @@ class ShardedCLIPPER(CLIPPER):
         _capi.check(self._h, self._lib.clp_shard_import(self._h, raw, nb, self.world))
         self._dist.barrier(group=self._group)
 
-    def score_pairwise_consistency(self, D1, D2, A=None):
+    def score_pairwise_consistency(self, D1, D2, A=None, balance=True):
+        """balance: relabel the associations so that every row shard holds about the same number of bytes (see
+        interleave_permutation); solve() maps nodes / u / u0 back, the caller never sees the relabelling"""
+        self._perm = None
+        if balance and A is not None and np.size(A) > 0 and self.world > 1:
+            self._perm = interleave_permutation(np.asarray(A).shape[0], self.world)
+            A, _ = permute_problem(A, None, self._perm)
         super().score_pairwise_consistency(D1, D2, A)
         m = self._m()
         if self._connected_for != m:
             self._connect()
             self._connected_for = m
+
+    def get_initial_associations(self):
+        A = super().get_initial_associations()
+        perm = getattr(self, "_perm", None)
+        return A if perm is None else np.asfortranarray(A[perm])
 
     def score_device(self, kind, D1, D2, A, *inv_params):
         """device-pointer scoring (torch tensors), same conventions as the C-ABI"""
@@ -133,8 +144,20 @@ class ShardedCLIPPER(CLIPPER):
 
     def solve(self, u0=None):
         """collective solve; a host barrier first, so that the in-kernel peer waits only ever cover kernel skew"""
+        if u0 is None:
+            raise ValueError("a sharded solve needs an explicit u0 (every rank must start from the same vector)")
+        perm = getattr(self, "_perm", None)
+        if perm is not None:
+            u0p = np.empty(len(perm), dtype=np.float64); u0p[perm] = np.asarray(u0, dtype=np.float64)
+        else:
+            u0p = u0
         self._dist.barrier(group=self._group)
-        super().solve(u0)
+        super().solve(u0p)
+        if perm is not None:
+            s = self._soln
+            s.nodes, s.u = unpermute_solution(s.nodes, s.u, perm)
+            s.nodes = s.nodes.tolist()
+            s.u0 = np.asarray(u0, dtype=np.float64).copy()
 
     def count_nonzeros(self):
         import torch
@@ -259,7 +282,11 @@ def run_bench(args, METRIC, UNIT):
     def one_workload(name, m_override, steps, warmup):
         prob = datagen.config_problem(name, m_override)
         cfg = prob["cfg"]; m = cfg["m"]
-        if os.environ.get("CLP_SHARD_INTERLEAVE") == "1":  # opt-in: byte-balance the shards (see interleave_permutation)
+        # byte-balanced shards: the generator puts the (denser) inlier associations last, so equal ROW counts give the last
+        # of 8 shards 1.14x the mean bytes; dealing the associations to the shards in proportion to their sizes (a
+        # relabelling of the same problem, see interleave_permutation) brings that to 1.01x.  CLP_SHARD_INTERLEAVE=0 keeps
+        # the generator's order.
+        if os.environ.get("CLP_SHARD_INTERLEAVE") != "0":
             prob["A"], prob["u0"] = permute_problem(prob["A"], prob["u0"], interleave_permutation(m, world))
         ip = clipperpy.invariants.EuclideanDistanceParams(); ip.sigma, ip.epsilon = cfg["sigma"], cfg["epsilon"]
         clip = ShardedCLIPPER(clipperpy.invariants.EuclideanDistance(ip), clipperpy.Params())
