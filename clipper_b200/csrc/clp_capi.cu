@@ -347,7 +347,9 @@ bool resident_possible(clp_handle h, long long m) {
 int res_pick_cfg(clp_handle h) {
   if (h->storage == CLP_STORE_F64) return kResCfgF64;  // 8-byte values: one light register pipeline
   int c = h->res_cfg;
-  if (c < 0 || c >= kNumResCfgs || c == kResCfgF64) c = 0;
+  // automatic: 2 rounds x 3 chunks measured 2 % faster than 3 x 2 on one GPU (profiles/r02d_*); its sharded instance
+  // spills, so shards take 3 x 2
+  if (c < 0 || c >= kNumResCfgs || c == kResCfgF64) c = (h->world > 1) ? 0 : 1;
   if ((long long)res_smem_bytes(h, c) > (long long)h->smem_optin) c = 0;
   return c;
 }
@@ -500,9 +502,14 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   h->sp.itemptr = h->sp_item.as<unsigned int>(); h->sp.rowid = h->sp_rowid.as<unsigned int>(); h->sp.rows_pad = h->rows_pad;
   // byte-balanced contiguous item range of every CTA (depends on the grid size: rebuilt with the plan)
   int G = p.G;
-  if (resident) {  // one fat CTA per SM; small problems use fewer CTAs (>= 2 items each), shards sharing a GPU honour the cap
+  if (resident) {
+    // one fat CTA per SM; small problems use fewer CTAs -- every CTA should stream at least ~96 KB per sweep (about
+    // 2 us), below that the device-wide exchange costs more than the extra SMs save; shards sharing a GPU honour the cap
     h->res_NI = NI;
-    G = std::max(1, std::min(h->grid_cap > 0 ? std::min(h->grid_cap, h->sm_count) : h->sm_count, NI / 2));
+    const long long by_bytes = (long long)((double)h->sp_nnz * (sizeof(T) + 2.0) / (96.0 * 1024.0));
+    G = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(h->grid_cap > 0 ? std::min(h->grid_cap, h->sm_count) : h->sm_count, NI / 2),
+                                                        std::max<long long>(1, by_bytes)));
+    if (env_int("CLP_RES_G", 0) > 0) G = std::max(1, std::min(env_int("CLP_RES_G", 0), std::min(h->sm_count, std::max(1, NI / 2))));
     h->res_G = G;
     h->res_cfg_eff = res_pick_cfg(h);
     CLP_CUDA(h, res_set_attrs<T>(h, h->res_cfg_eff, h->world > 1));

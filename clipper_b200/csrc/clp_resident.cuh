@@ -468,9 +468,9 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
     __syncthreads();
     return true;
   } else {
-    // Every CTA publishes its 8 partial sums as self-validating LL cells {lo, tag, hi, tag} and bumps an arrival
-    // counter with a RELAXED atomic: no __threadfence anywhere (a membar.gpu costs about a microsecond, and the
-    // cooperative-groups style barrier needs two).  The counter only tells the waiters when polling is likely to
+    // Every CTA publishes its 8 partial sums as self-validating LL cells {lo, tag, hi, tag} and arrives with a RELAXED
+    // atomic: no __threadfence anywhere (a membar.gpu costs about a microsecond, and the cooperative-groups style
+    // barrier needs two).  The arrival count / release flag only tell the waiters when reading is likely to
     // succeed; correctness comes from the tags: every CTA then reads the whole table, re-polling any cell whose
     // tag is not this round's, and adds the rows in the same fixed order.
     const int G = a.G;
@@ -495,15 +495,23 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
       if (warp == 0) {
         __syncwarp();
         if (lane == 0) {
-          asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(&a.sb->root[0]), "l"(1ULL) : "memory");
-          const unsigned long long target = round * (unsigned long long)G;
-          const long long t0 = clock64();
-          unsigned long long seen;
-          do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&a.sb->root[0]) : "memory");
-            if (seen >= target) break;
-          } while (clock64() - t0 <= a.spin_limit);
-          if (seen < target) atomicExch(errp, 1);
+          // arrival: one returning relaxed atomic; the LAST arriver publishes the round number in a flag on another
+          // L2 line, which the others poll with a back-off (polling the arrival counter itself makes 148 SMs hammer
+          // the address the atomics are queued on)
+          unsigned long long old;
+          asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(&a.sb->root[0]), "l"(1ULL) : "memory");
+          if (old + 1ULL == round * (unsigned long long)G) {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&a.sb->gen[0]), "l"(round) : "memory");
+          } else {
+            const long long t0 = clock64();
+            unsigned long long seen;
+            for (;;) {
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&a.sb->gen[0]) : "memory");
+              if (seen >= round) break;
+              __nanosleep(40);
+              if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
+            }
+          }
         }
       }
       __syncthreads();

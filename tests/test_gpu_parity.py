@@ -472,9 +472,11 @@ def test_dense_modes_agree(clp, orc, m, storage):
         # the segmented kernels share every O(m) statement and differ only in how a row's products are grouped; the
         # resident kernel also groups the scalar reductions differently, so its trajectory agrees to rounding (1e-12 per
         # step) and its final objective to well below the solver's own stopping tolerance tol_F = 1e-9
+        # (1e-12 held for every case on the round-1 synthetic cloud; on the bunny cloud the m = 4500 case reaches 4e-12
+        # between two segmented sweeps: the differences are rounding noise amplified along ~70 evaluations)
         same_kernel = effective[k] in (0, 1, 2, 3)
-        assert abs(sk.score - s0.score) <= (1e-12 if same_kernel else 2e-11) * abs(s0.score)
-        assert np.abs(sk.u - s0.u).max() <= (1e-12 if same_kernel else 1e-10)
+        assert abs(sk.score - s0.score) <= (1e-11 if same_kernel else 2e-11) * abs(s0.score)
+        assert np.abs(sk.u - s0.u).max() <= (1e-11 if same_kernel else 1e-10)
     for _, _, _, s in res:
         assert sorted(s.nodes) == sorted(so.nodes.tolist())
         assert abs(s.score - so.score) <= (1e-9 if storage == 1 else 1e-5) * abs(so.score)
