@@ -320,9 +320,10 @@ void res_pick_caps(clp_handle h, int c, unsigned int* pieces_cap, unsigned int* 
   if (!h->res_smem_extra || h->res_G < 1) return;
   const ResCfg& k = kResCfgs[c];
   const unsigned int items = (unsigned int)((h->res_NI + h->res_G - 1) / h->res_G);
-  unsigned int pc = items + items / 2 + 4 + (unsigned int)(k.NT / 32), sc = 4 * (items + items / 2 + 4);
+  // the partition is balanced by bytes, so CTAs holding short rows hold more items than the mean: 2x the mean + slack
+  unsigned int pc = 2 * items + 8 + (unsigned int)(k.NT / 32), sc = 4 * (2 * items + 8);
   const unsigned int base = res_smem_plan((int)h->m, k.NT / 32, k.ring ? k.D : 0, k.U, (int)h->esize()).total;
-  const unsigned int budget = std::min<unsigned int>(24u << 10, (unsigned int)std::max(0, h->smem_optin - (int)base - 256));
+  const unsigned int budget = std::min<unsigned int>(32u << 10, (unsigned int)std::max(0, h->smem_optin - (int)base - 256));
   if (pc * 64u + sc * 72u > budget) {  // keep the piece table first, then as much row state as fits -- or none
     if (pc * 64u > budget) return;
     sc = 0;
@@ -356,7 +357,9 @@ int res_pick_cfg(clp_handle h) {
 
 template <typename T>
 cudaError_t res_set_attrs(clp_handle h, int c, bool sharded) {
-  const int bytes = (int)res_launch_smem(h, c);
+  // the attribute is a per-function PERMISSION shared by every handle of the process (two shards in one process ask
+  // for different sizes): always the device maximum; the carve-out follows what each launch actually requests
+  const int bytes = h->smem_optin;
   return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
     if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
     else {

@@ -116,7 +116,7 @@ __host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages,
   s.off_fin = o; o += (unsigned int)((2 + kMaxPeers) * kRedVals * 8);
   s.off_wb = o; o += (unsigned int)((NW + 1) * 4);
   o = (o + 7u) & ~7u;
-  s.off_misc = o; o += 128;   // per-warp phase bits of the ring's mbarriers (persist from sweep to sweep)
+  s.off_misc = o; o += 128 + (unsigned int)NW * 8;  // per-warp: phase bits of the ring's mbarriers (persist across sweeps) | start of its stream (item, end)
   s.off_bar = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages * 8 : 0);
   o = (o + 127u) & ~127u;
   s.stage_bytes = res_round_bytes(U, esize);
@@ -302,10 +302,21 @@ __device__ void res_sweep(const ResArgs& a, const int bid, const double* vs, uns
   const unsigned int padk = (unsigned int)a.m | ((unsigned int)a.m << 16);  // column m holds 0.0
   double* pieces = ptab + (size_t)warp * kPieceVals;  // + (item - isub) * 8
 
-  // ---- producer cursor (warp-uniform): the piece being loaded
-  unsigned int cit = res_item_of(itemptr, it0, it1 - 1, s0);
+  // ---- producer cursor (warp-uniform): the piece being loaded.  Where a warp's stream starts never changes during a
+  // solve: found once (binary search over the item pointers = a chain of dependent L2 loads) and kept in shared memory
+  uint2* wstart = reinterpret_cast<uint2*>(smem + plan.off_misc + 128) + warp;
+  unsigned int cit, ce;
+  {
+    const uint2 w = *wstart;
+    if (w.y != 0u) { cit = w.x; ce = w.y; }
+    else {
+      cit = res_item_of(itemptr, it0, it1 - 1, s0);
+      ce = min(itemptr[cit + 1], s1);
+      __syncwarp();
+      if (lane == 0) *wstart = make_uint2(cit, ce);   // ce > s0 >= 0: never 0
+    }
+  }
   unsigned int cj = s0;
-  unsigned int ce = min(itemptr[cit + 1], s1);
   bool pdone = false;
   double aM[2] = {0.0, 0.0}, aC[2] = {0.0, 0.0};
 
@@ -508,7 +519,7 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
             for (;;) {
               asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&a.sb->gen[0]) : "memory");
               if (seen >= round) break;
-              __nanosleep(40);
+              __nanosleep(20);
               if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
             }
           }
@@ -605,6 +616,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     const unsigned int c_lo = a.sp.itemptr[it0], c_hi = a.sp.itemptr[it1];
     wb[threadIdx.x] = res_warp_bound(c_lo, c_hi, threadIdx.x, NW);
   }
+  if (threadIdx.x < NW) reinterpret_cast<uint2*>(smem + plan.off_misc + 128)[threadIdx.x] = make_uint2(0u, 0u);
   if constexpr (RING) {
     if (threadIdx.x < NW * D) mbar_init(reinterpret_cast<unsigned long long*>(smem + plan.off_bar) + threadIdx.x, 1);
     if (threadIdx.x < NW) reinterpret_cast<unsigned int*>(smem + plan.off_misc)[threadIdx.x] = 0u;
@@ -869,6 +881,7 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
   const int bid = (int)blockIdx.x;
   const unsigned int it0 = a.sp.cta_first[bid], it1 = a.sp.cta_first[bid + 1];
   if (threadIdx.x <= NW) wb[threadIdx.x] = res_warp_bound(a.sp.itemptr[it0], a.sp.itemptr[it1], threadIdx.x, NW);
+  if (threadIdx.x < NW) reinterpret_cast<uint2*>(smem + plan.off_misc + 128)[threadIdx.x] = make_uint2(0u, 0u);
   if constexpr (RING) {
     if (threadIdx.x < NW * D) mbar_init(reinterpret_cast<unsigned long long*>(smem + plan.off_bar) + threadIdx.x, 1);
     if (threadIdx.x < NW) reinterpret_cast<unsigned int*>(smem + plan.off_misc)[threadIdx.x] = 0u;
