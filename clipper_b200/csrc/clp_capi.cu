@@ -96,12 +96,14 @@ struct clp_handle_s {
   int res_cfg_eff = 0;
   int res_smem_extra = env_int("CLP_RES_SMEM_EXTRA", 1);  // 0: launch with the plan's minimum (piece table / row state in HBM)
   int prof_ctas = env_int("CLP_PROF_CTAS", 0);      // print the per-CTA phase times of every resident solve (stderr)
+  int prof_host = env_int("CLP_PROF_HOST", 0);      // print wall-clock marks of the scoring / solve calls (stderr)
   DevBuf prof_buf;
   int res_G = 0;                                    // CTAs of the resident kernels for the current matrix
   int res_NI = 0;
   bool compact_resident = false;                    // layout of the current compact copy: full rows + column indices
   int smem_optin = 0;                               // cudaDevAttrMaxSharedMemoryPerBlockOptin
   int fuse_count = env_int("CLP_FUSE_COUNT", 1);  // scoring kernel counts the kept entries (skips sparse_count_kernel)
+  bool score_pending = false;                       // a scoring launch's error flag has not been read back yet
   bool counts_fused = false;                        // sp_ptr4 already holds the counts of the current matrix
   long long counts_m = 0; int counts_rows_pad = 0, counts_nseg = 0, counts_W = 0;  // ... which was this one
   int fill_items = env_int("CLP_FILL_ITEMS", 1);  // compact copy written item-wise (coalesced) instead of row-wise
@@ -357,6 +359,10 @@ int res_pick_cfg(clp_handle h) {
 
 template <typename T>
 cudaError_t res_set_attrs(clp_handle h, int c, bool sharded) {
+  static bool done[2][kNumResCfgs][2][8] = {};  // [storage][configuration][sharded][device]: set once per process
+  bool& flag = done[sizeof(T) == 8 ? 1 : 0][c][sharded ? 1 : 0][h->device & 7];
+  if (flag) return cudaSuccess;
+  flag = true;
   // the attribute is a per-function PERMISSION shared by every handle of the process (two shards in one process ask
   // for different sizes): always the device maximum; the carve-out follows what each launch actually requests
   const int bytes = h->smem_optin;
@@ -443,7 +449,11 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   const bool fused = h->counts_fused && h->counts_m == h->m && h->counts_rows_pad == h->rows_pad &&
                      h->counts_nseg == nseg && h->counts_W == p.W;
   h->counts_fused = false;
-  if (int rc = reset_sync(h)) return rc;
+  // right after a scoring launch the sync block still carries that launch's error flag (checked below, with the
+  // totals: one host synchronisation per scoring call) and zeroed counters; otherwise start from a clean block
+  const bool after_score = h->score_pending;
+  h->score_pending = false;
+  if (!after_score) { if (int rc = reset_sync(h)) return rc; }
   SyncBlock* sb = h->sync.as<SyncBlock>();
   const T* M = h->Mbuf.as<T>();
   const unsigned blocks = (unsigned)(((size_t)h->rows_pad * 32 + 255) / 256);
@@ -475,9 +485,12 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   sparse_scan_fix_kernel<<<nseg, 1024, 0, h->stream>>>(h->sp_item.as<unsigned int>(), NI + 1, nseg, segtot_d, total4_d);
   CLP_CUDA(h, cudaGetLastError());
   unsigned long long host[3] = {0, 0, 0};
+  int host_err = 0;
   CLP_CUDA(h, cudaMemcpyAsync(&host[0], total4_d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CLP_CUDA(h, cudaMemcpyAsync(&host[1], &sb->counts[0], 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  if (after_score) CLP_CUDA(h, cudaMemcpyAsync(&host_err, &sb->error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (host_err == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
   const unsigned long long n4 = host[0];
   if (n4 >= 0xffffffffull) { if (force) return fail(h, CLP_ERR_UNSUPPORTED, "compact rows: too many entries"); return 1; }
   h->sp_nnz = 4 * n4;        // stored entries (incl. the padding of slices and items): what one pass reads
@@ -653,6 +666,7 @@ int launch_score(clp_handle h, int kind, int d, const ScoreArgs& a) {
 // common tail of the four scoring entry points: D1/D2/A already on the device
 int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long n1, const double* D2d,
                     long long n2, const int32_t* Ad, long long m, double p0, double p1, double p2, double p3) {
+  const auto tp0 = std::chrono::steady_clock::now();
   if (int rc = ensure_matrix(h, m)) return rc;
   CLP_CUDA(h, h->E1.ensure((size_t)m * d * sizeof(double)));
   CLP_CUDA(h, h->E2.ensure((size_t)m * d * sizeof(double)));
@@ -684,16 +698,29 @@ int score_on_device(clp_handle h, int kind, const double* D1d, int d, long long 
   a.d = d; a.p0 = p0; a.p1 = p1; a.p2 = p2; a.p3 = p3; a.affinityeps = h->prm.affinityeps;
   int rc = (h->storage == CLP_STORE_F64) ? launch_score<double>(h, kind, d, a) : launch_score<float>(h, kind, d, a);
   if (rc) return rc;
-  SyncBlock host;
-  if ((rc = read_sync(h, &host))) return rc;
-  if (host.error == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
-  if (a.cnt) {  // the scoring kernel is known to have completed: its counts describe this matrix
+  const bool compact_next = (h->dense_mode == 3 || h->dense_mode == 4 || h->dense_mode == 6);
+  if (!compact_next) {  // dense sweeps: nothing else synchronises with the scoring launch
+    SyncBlock host;
+    if ((rc = read_sync(h, &host))) return rc;
+    if (host.error == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
+  } else {
+    h->score_pending = true;  // the compact build reads the flag back together with its totals
+  }
+  const auto tp1 = std::chrono::steady_clock::now();
+  if (a.cnt) {  // counts produced by this launch describe this matrix (a failed launch / bad index aborts the build)
     h->counts_fused = true;
     h->counts_m = m; h->counts_rows_pad = h->rows_pad; h->counts_nseg = cnt_nseg; h->counts_W = cnt_W;
   }
-  if ((rc = finalize_matrix(h))) return rc;
+  rc = finalize_matrix(h);
+  h->score_pending = false;
+  if (rc) { h->counts_fused = false; return rc; }
   h->has_matrix = true;
   h->has_A = true;
+  if (h->prof_host) {
+    const auto tp2 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[clp host] score call: scoring kernel done after %.3f ms, build enqueued after %.3f ms (total)\n",
+                 1e3 * std::chrono::duration<double>(tp1 - tp0).count(), 1e3 * std::chrono::duration<double>(tp2 - tp0).count());
+  }
   return CLP_OK;
 }
 
@@ -843,6 +870,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   if (u_out_dev)
     CLP_CUDA(h, cudaMemcpyAsync(u_out_dev, a.u_final, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  const auto tp_sync = std::chrono::steady_clock::now();
   float ms = 0.f;
   CLP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 
@@ -914,6 +942,10 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
 
     out->t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   }
+  if (h->prof_host)
+    std::fprintf(stderr, "[clp host] solve call: results on the host after %.3f ms (solver kernel %.3f ms), rounding done after %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(tp_sync - t_begin).count(), ms,
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
   return CLP_OK;
 }
 

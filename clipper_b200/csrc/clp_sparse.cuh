@@ -314,30 +314,40 @@ __device__ __forceinline__ void sell_fill_item_warp(const T* M, long long ld, in
   };
   for (int j0 = c0; j0 < c1; j0 += 128) {
     const int j = j0 + lane * 4;
+    // the four members' 128 columns: all loads first, then ONE warp scan for the four kept-entry counts (packed
+    // as four 8-bit fields: a member keeps at most 128 entries per step)
+    T x[4][4];
+    unsigned int keep[4], packed = 0u;
 #pragma unroll
     for (int s_ = 0; s_ < 4; ++s_) {
-      if (r[s_] >= (unsigned int)rows) continue;  // warp-uniform
-      T x[4];
-      load4<T>(M + (size_t)r[s_] * ld + j, x);  // j + 3 < ld: ld is a multiple of 128
-      unsigned int keep = 0;
+      if (r[s_] < (unsigned int)rows) load4<T>(M + (size_t)r[s_] * ld + j, x[s_]);  // j + 3 < ld: ld is a multiple of 128
+      else { x[s_][0] = x[s_][1] = x[s_][2] = x[s_][3] = encode<T>(0.0, false); }
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < 4; ++s_) {
+      keep[s_] = 0u;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (j + q >= c1) x[q] = encode<T>(0.0, false);
-        keep |= (!is_neutral<T>(x[q]) ? 1u : 0u) << q;
+        if (j + q >= c1) x[s_][q] = encode<T>(0.0, false);
+        keep[s_] |= (!is_neutral<T>(x[s_][q]) ? 1u : 0u) << q;
       }
-      const unsigned int cnt = __popc(keep);
-      unsigned int pre = cnt;  // inclusive scan over lanes
+      packed |= (unsigned int)__popc(keep[s_]) << (8 * s_);
+    }
+    unsigned int pre = packed;  // inclusive scan over lanes, four fields at once (no carry: every field stays <= 128)
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int y = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += y;
-      }
-      const unsigned int total = __shfl_sync(0xffffffffu, pre, 31);
-      unsigned int w = n[s_] + (pre - cnt);
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += y;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, pre, 31);
+    const unsigned int excl = pre - packed;
+#pragma unroll
+    for (int s_ = 0; s_ < 4; ++s_) {
+      unsigned int w = n[s_] + ((excl >> (8 * s_)) & 0xffu);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (keep & (1u << q)) { rv[s_][w & (kRing - 1)] = x[q]; ro[s_][w & (kRing - 1)] = (unsigned short)((j + q - c0) << off_shift); ++w; }
-      n[s_] += total;
+        if (keep[s_] & (1u << q)) { rv[s_][w & (kRing - 1)] = x[s_][q]; ro[s_][w & (kRing - 1)] = (unsigned short)((j + q - c0) << off_shift); ++w; }
+      n[s_] += (total >> (8 * s_)) & 0xffu;
     }
     __syncwarp();
     // flush 8 complete chunks of every member that has them (members of an item have almost the same length:
