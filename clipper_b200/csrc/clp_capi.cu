@@ -435,6 +435,8 @@ cudaError_t launch_resident_matvec(clp_handle h, const double* v, double d, doub
   });
 }
 
+constexpr int kKeepDense = -1;  // build_sparse: the compact copy would not pay off (NOT an error code)
+
 // Called once the dense store holds the new matrix: pick the sweep (dense mode) and build what it needs.
 template <typename T>
 int build_sparse(clp_handle h, bool force, bool resident) {
@@ -492,14 +494,14 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   CLP_CUDA(h, cudaStreamSynchronize(h->stream));
   if (host_err == 2) return fail(h, CLP_ERR_INVALID, "association index out of range of D1/D2");
   const unsigned long long n4 = host[0];
-  if (n4 >= 0xffffffffull) { if (force) return fail(h, CLP_ERR_UNSUPPORTED, "compact rows: too many entries"); return 1; }
+  if (n4 >= 0xffffffffull) { if (force) return fail(h, CLP_ERR_UNSUPPORTED, "compact rows: too many entries"); return kKeepDense; }
   h->sp_nnz = 4 * n4;        // stored entries (incl. the padding of slices and items): what one pass reads
   h->sp_nnz_real = host[1];  // non-neutral entries of the local rows
   h->sp.plain = host[2] == 0 ? 1 : 0;
   // worth it?  compare with the bytes of the best dense sweep (upper triangle two-sided on one GPU, full rows when sharded)
   const double sparse_bytes = (double)h->sp_nnz * (sizeof(T) + 2.0);
   const double dense_bytes = (h->world > 1) ? (double)sizeof(T) * h->rows * (double)h->m : 0.5 * sizeof(T) * (double)h->m * (double)h->m;
-  if (!force && !(sparse_bytes < 0.8 * dense_bytes)) return 1;  // keep a dense sweep
+  if (!force && !(sparse_bytes < 0.8 * dense_bytes)) return kKeepDense;  // keep a dense sweep
   CLP_CUDA(h, h->sp_val.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(T)));
   CLP_CUDA(h, h->sp_col.ensure((size_t)std::max<unsigned long long>(h->sp_nnz, 4) * sizeof(unsigned short)));
   if (resident || (h->fill_items && !std::getenv("CLP_PROBE_NO_CONFLICT"))) {
@@ -574,7 +576,7 @@ int finalize_matrix_impl(clp_handle h) {
     const bool force = (eff == 3) || (eff == 6);
     const int rc = (h->storage == CLP_STORE_F64) ? build_sparse<double>(h, force, resident) : build_sparse<float>(h, force, resident);
     if (rc == CLP_OK) eff = resident ? 6 : 3;
-    else if (rc == 1) eff = (h->world > 1) ? 0 : 2;
+    else if (rc == kKeepDense) eff = (h->world > 1) ? 0 : 2;
     else return rc;
   }
   if (eff == 2 && h->world > 1) eff = 1;
@@ -879,8 +881,8 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   if (h->prof_ctas && h->dense_mode_eff == 6) {  // diagnostics: spread of the per-CTA phase times
     std::vector<double> pc((size_t)h->res_G * 4);
     CLP_CUDA(h, cudaMemcpy(pc.data(), h->prof_buf.p, pc.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    const char* nm[3] = {"sweeps", "epilogues", "exchanges"};
-    for (int q = 0; q < 3; ++q) {
+    const char* nm[4] = {"sweeps", "epilogues", "exchanges", "staging"};
+    for (int q = 0; q < 4; ++q) {
       double lo = 1e300, hi = 0, sum = 0;
       for (int b = 0; b < h->res_G; ++b) { const double x = pc[(size_t)b * 4 + q]; lo = std::min(lo, x); hi = std::max(hi, x); sum += x; }
       std::fprintf(stderr, "[clp prof] %-9s per solve: min %.3f  mean %.3f  max %.3f ms over %d CTAs (%lld evaluations)\n", nm[q],

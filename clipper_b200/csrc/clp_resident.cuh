@@ -684,7 +684,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0;
   unsigned long long round = 0, seq = a.seq0;
   unsigned int ctag = 0u;  // tag under which the candidates of parity cpar were written
-  unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, tmark = global_ns();
+  unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, ns_st = 0, tmark = global_ns();
 #define RES_LAP(acc) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; }
 #define RES_ZERO() _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
 #define RES_FOR_ROWS(i, itx, sx)                                                                    \
@@ -704,6 +704,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   {
     if (P.rescale_u0) {
       res_stage<NT, SHARDED>(RS_RAW, m, a.u0, nullptr, 0u, 1.0, vs, red_s, fin, errp, a.spin_limit);
+      RES_LAP(ns_st);
       RES_SWEEP();
     }
     RES_ZERO();
@@ -727,6 +728,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
                                                SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
                                                errp, a.spin_limit);
+    RES_LAP(ns_st);
     RES_SWEEP();
     cur = 1;
     sum_cur = sumu;
@@ -772,6 +774,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
         const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
                                                    vs, red_s, fin, errp, a.spin_limit);
+        RES_LAP(ns_st);
         RES_SWEEP();
         ++n_evals;
         // per-row epilogue: gradFnew, Fnew, |unew - u|^2 and BOTH possible next trial points
@@ -845,13 +848,13 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
 finish:
   if (a.prof_cta && threadIdx.x == 0) {
     a.prof_cta[(size_t)bid * 4 + 0] = (double)ns_mv; a.prof_cta[(size_t)bid * 4 + 1] = (double)ns_cb;
-    a.prof_cta[(size_t)bid * 4 + 2] = (double)ns_ex; a.prof_cta[(size_t)bid * 4 + 3] = (double)(it1 - it0);
+    a.prof_cta[(size_t)bid * 4 + 2] = (double)ns_ex; a.prof_cta[(size_t)bid * 4 + 3] = (double)ns_st;
   }
   if (bid == 0 && threadIdx.x == 0) {
     if (*reinterpret_cast<volatile int*>(errp) != 0) status = 5;
     a.out->F = F; a.out->d = d; a.out->ifinal = i_outer; a.out->cur = cur; a.out->status = status;
     a.out->n_evals = n_evals; a.out->n_inner = n_inner; a.out->n_matvec = n_matvec; a.out->seq_end = seq;
-    a.out->ns_matvec = ns_mv; a.out->ns_combine = ns_cb; a.out->ns_exchange = ns_ex;
+    a.out->ns_matvec = ns_mv + ns_st; a.out->ns_combine = ns_cb; a.out->ns_exchange = ns_ex;
   }
 #undef RES_LAP
 #undef RES_ZERO

@@ -138,15 +138,10 @@ __global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, int nb,
   __syncthreads();
   // STABLE placement (ties in row order): the layout -- hence the grouping of every fp64 sum downstream -- must not
   // depend on the arrival order of atomics, or two runs on the same input differ in the last bit.  Rows are taken in
-  // tiles of blockDim.x in row order; the warps update the class counters strictly in (tile, warp) order, passing a
-  // ticket through shared memory; inside a warp __match_any_sync ranks the lanes of equal length class.
+  // tiles of blockDim.x in row order; inside a tile the warps take turns (one __syncthreads per turn); inside a warp
+  // __match_any_sync ranks the lanes of equal length class.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  __shared__ volatile unsigned int turn;   // ticket of the warp whose turn it is (tile * nwarp + warp)
-  if (threadIdx.x == 0) turn = 0u;
-  __syncthreads();
-  volatile unsigned int* vhist = hist;
-  unsigned int ticket = (unsigned int)warp;
-  for (int base = 0; base < rows_pad; base += blockDim.x, ticket += (unsigned int)nwarp) {
+  for (int base = 0; base < rows_pad; base += blockDim.x) {
     const int r = base + threadIdx.x;
     const bool have = r < rows_pad;
     const unsigned int cls = have ? min((c[r] + 3u) >> 2, (unsigned int)(nb - 1)) : 0xffffffffu;
@@ -154,12 +149,10 @@ __global__ void sell_sort_kernel(const unsigned int* cnt4, int rows_pad, int nb,
     const int leader = __ffs(peers) - 1;
     const unsigned int before = __popc(peers & ((1u << lane) - 1u));
     unsigned int start = 0u;
-    if (lane == 0) { unsigned int spins = 0u; while (turn != ticket && ++spins < (1u << 28)) {} }  // turns in ticket order (all warps resident: one block); bounded
-    __syncwarp();
-    if (have && lane == leader) { start = vhist[cls]; vhist[cls] = start + __popc(peers); }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) turn = ticket + 1u;
+    for (int w = 0; w < nwarp; ++w) {   // the warps of the tile take turns (measured: 89 us at m = 20 000; passing a
+      if (warp == w && have && lane == leader) { start = hist[cls]; hist[cls] = start + __popc(peers); }  // ticket
+      __syncthreads();                  // through shared memory with spinning warps took 683 us)
+    }
     start = __shfl_sync(0xffffffffu, start, leader);
     if (have) {
       const unsigned int pos = start + before;
