@@ -399,6 +399,7 @@ ResArgs res_args(clp_handle h) {
   a.comm = h->comm.as<CommBlock>();
   for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
   a.spin_limit = (long long)h->spin_seconds * 1900000000LL;
+  a.ll_gpu_scope = env_int("CLP_LL_GPU_SCOPE", 1);
   a.ring_stages = kResCfgs[h->res_cfg_eff].ring ? kResCfgs[h->res_cfg_eff].D : 0;
   res_pick_caps(h, h->res_cfg_eff, &a.pieces_cap, &a.state_cap);
   a.redll = h->res_redll.as<uint4>();

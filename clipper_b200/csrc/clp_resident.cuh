@@ -59,6 +59,7 @@ struct ResArgs {
   CommBlock* peer_comm[kMaxPeers];
   unsigned long long seq0;
   long long spin_limit;    // clock64 ticks a wait may last before it raises the time-out flag
+  int ll_gpu_scope;        // sharded staging: first look at an LL cell with a gpu-scope load (1) or a system-scope one (0)
   int ring_stages;         // > 0: cp.async.bulk ring with this many stages per warp (RING instances)
   unsigned int pieces_cap, state_cap;  // on-chip piece table (entries) / row state (rows) per CTA, 0: keep them in HBM
   uint4* redll;            // [2][G][8] per-CTA partial sums as self-validating LL cells (zeroed before the launch)
@@ -189,9 +190,20 @@ __device__ __forceinline__ void res_publish(const double (&loc)[kRedVals], doubl
 //   RS_DIV : v = w / |w|                               (u /= u.norm(), clipper.cpp:198 -- no zero guard)
 //   RS_STEP: v = w / |w| if |w|^2 > 0 else w           (unew.normalize(), clipper.cpp:237), w = a candidate point
 // ---------------------------------------------------------------------------------------------------------------
+// LL cell load.  The cells live in LOCAL memory (peers store into it over NVLink, the home L2 is the point of
+// coherence for every writer), so a gpu-scope relaxed load observes them; GPU_SCOPE = false uses the system-scope
+// (volatile) load of the classic LL protocol.
+template <bool GPU_SCOPE>
+__device__ __forceinline__ void ll_ld4(const uint4* p, unsigned int& lo, unsigned int& t1, unsigned int& hi, unsigned int& t2) {
+  if constexpr (GPU_SCOPE)
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+  else
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+}
+
 template <int NT, bool SHARDED>
 __device__ double res_stage(int mode, int m, const double* src, const uint4* cells, unsigned int tag, double z,
-                            double* vs, double* red_s, double* fin, int* errp, long long spin_limit) {
+                            double* vs, double* red_s, double* fin, int* errp, long long spin_limit, int ll_gpu_scope = 0) {
   const double nrm = sqrt(z);
   const double rinv = 1.0 / nrm;
   const bool scale = (mode == RS_DIV) || (mode == RS_STEP && z > 0.0);
@@ -205,9 +217,7 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
       for (int b = 0; b < kB; ++b) {
         const int j = j0 + b * NT;
         lo[b] = hi[b] = 0u; t1[b] = t2[b] = tag;
-        if (j < m)
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(lo[b]), "=r"(t1[b]), "=r"(hi[b]), "=r"(t2[b]) : "l"(cells + j) : "memory");
+        if (j < m) { if (ll_gpu_scope) ll_ld4<true>(cells + j, lo[b], t1[b], hi[b], t2[b]); else ll_ld4<false>(cells + j, lo[b], t1[b], hi[b], t2[b]); }
       }
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
@@ -218,8 +228,7 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
           else {  // not there yet: poll (bounded)
             long long t0 = 0;
             for (;;) {
-              asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(lo[b]), "=r"(t1[b]), "=r"(hi[b]), "=r"(t2[b]) : "l"(cells + j) : "memory");
+              ll_ld4<false>(cells + j, lo[b], t1[b], hi[b], t2[b]);
               if (t1[b] == tag && t2[b] == tag) break;
               if (t0 == 0) t0 = clock64();
               else if (clock64() - t0 > spin_limit) { atomicExch(errp, 1); break; }
@@ -479,11 +488,10 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
     __syncthreads();
     return true;
   } else {
-    // Every CTA publishes its 8 partial sums as self-validating LL cells {lo, tag, hi, tag} and arrives with a RELAXED
-    // atomic: no __threadfence anywhere (a membar.gpu costs about a microsecond, and the cooperative-groups style
-    // barrier needs two).  The arrival count / release flag only tell the waiters when reading is likely to
-    // succeed; correctness comes from the tags: every CTA then reads the whole table, re-polling any cell whose
-    // tag is not this round's, and adds the rows in the same fixed order.
+    // Every CTA publishes its 8 partial sums as self-validating LL cells {lo, tag, hi, tag} and arrives with one
+    // acq_rel atomic; the last arriver releases a flag on another L2 line which the others poll (acquire, back-off).
+    // Every CTA then reads the whole table -- a cell whose tag is not this round's is re-polled -- and adds the rows
+    // in the same fixed order: no last-arriver serial reduction, no second release hop.
     const int G = a.G;
     uint4* table = a.redll + (size_t)red_par * G * kRedVals;
     const unsigned int rtag = (unsigned int)round;
@@ -509,15 +517,18 @@ __device__ bool res_exchange(const ResArgs& a, const int bid, const double (&loc
           // arrival: one returning relaxed atomic; the LAST arriver publishes the round number in a flag on another
           // L2 line, which the others poll with a back-off (polling the arrival counter itself makes 148 SMs hammer
           // the address the atomics are queued on)
+          // acq_rel / release / acquire at gpu scope: the epilogue's PLAIN stores (candidate points of the unsharded
+          // solve, read by every CTA when it stages the next trial vector) are ordered before the arrival through the
+          // __syncthreads above (causality order) and become visible to whoever observes the flag
           unsigned long long old;
-          asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(&a.sb->root[0]), "l"(1ULL) : "memory");
+          asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(&a.sb->root[0]), "l"(1ULL) : "memory");
           if (old + 1ULL == round * (unsigned long long)G) {
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&a.sb->gen[0]), "l"(round) : "memory");
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&a.sb->gen[0]), "l"(round) : "memory");
           } else {
             const long long t0 = clock64();
             unsigned long long seen;
             for (;;) {
-              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&a.sb->gen[0]) : "memory");
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&a.sb->gen[0]) : "memory");
               if (seen >= round) break;
               __nanosleep(20);
               if (clock64() - t0 > a.spin_limit) { atomicExch(errp, 1); break; }
@@ -727,7 +738,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   {
     const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
                                                SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
-                                               errp, a.spin_limit);
+                                               errp, a.spin_limit, a.ll_gpu_scope);
     RES_LAP(ns_st);
     RES_SWEEP();
     cur = 1;
@@ -773,7 +784,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         // trial point into shared memory, sweep of the CTA's rows
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
         const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
-                                                   vs, red_s, fin, errp, a.spin_limit);
+                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope);
         RES_LAP(ns_st);
         RES_SWEEP();
         ++n_evals;
