@@ -1279,6 +1279,10 @@ int clp_matvec_dev(clp_handle h, const double* v_dev, double d, double* y_dev, d
   if (!h->has_matrix) return fail(h, CLP_ERR_INVALID, "no affinity matrix");
   if (h->world > 1) return fail(h, CLP_ERR_UNSUPPORTED, "clp_matvec_dev on a sharded handle");
   CLP_CUDA(h, cudaSetDevice(h->device));
+  if ((reinterpret_cast<uintptr_t>(v_dev) & 15u) != 0) {  // the kernels read v with 16-byte loads
+    CLP_CUDA(h, cudaMemcpyAsync(h->ybuf.p, v_dev, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    v_dev = h->ybuf.as<double>();
+  }
   CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   for (int r = 0; r < reps; ++r)
     if (int rc = matvec_enqueue(h, v_dev, d, y_dev, Mv_dev, Cv_dev)) return rc;

@@ -203,60 +203,93 @@ __device__ __forceinline__ void ll_ld4(const uint4* p, unsigned int& lo, unsigne
 
 template <int NT, bool SHARDED>
 __device__ double res_stage(int mode, int m, const double* src, const uint4* cells, unsigned int tag, double z,
-                            double* vs, double* red_s, double* fin, int* errp, long long spin_limit, int ll_gpu_scope = 0) {
+                            double* vs, double* red_s, double* fin, int* errp, long long spin_limit, int ll_gpu_scope = 0,
+                            int rot = 0) {
+  // Every CTA of the grid reads the SAME m values at the same moment.  Measured on B200 (profiles/r02i): with all 148
+  // CTAs walking the vector in the same order, four 8-byte loads in flight per thread, this step took 14.7 us per
+  // evaluation at m = 20 000 -- a fifth of the solver -- while the sweep itself ran at the HBM peak.  So: 16-byte
+  // loads, eight of them in flight per thread, and every CTA starts at a different place (rot) so that the SMs do not
+  // queue on the same L2 lines; the sum is then taken in a CTA-independent order from shared memory.
   const double nrm = sqrt(z);
   const double rinv = 1.0 / nrm;
   const bool scale = (mode == RS_DIV) || (mode == RS_STEP && z > 0.0);
-  double part = 0.0;
-  constexpr int kB = 4;  // loads in flight per thread
-  for (int j0 = threadIdx.x; j0 < m; j0 += kB * NT) {
-    double w[kB];
-    if (SHARDED && mode != RS_RAW) {
-      unsigned int lo[kB], t1[kB], hi[kB], t2[kB];
+  const int npair = (m + 1) >> 1;
+  const int K = (npair + NT - 1) / NT;          // pair slots per thread
+  const int span = K * NT;
+  const int r0 = ((rot % span) + span) % span & ~31;  // whole warps stay contiguous
+  auto finish = [&](int j, double w) {            // element j of the vector
+    if (j < m) {
+      double v = w;
+      if (scale) v = (mode == RS_DIV) ? (w / nrm) : div_by_invariant(w, nrm, rinv);
+      vs[j] = v;
+    }
+  };
+  if (SHARDED && mode != RS_RAW) {
+    constexpr int kB = 4;  // pairs (= 2 LL cells each) in flight per thread
+    for (int k0 = 0; k0 < K; k0 += kB) {
+      unsigned int lo[2 * kB], t1[2 * kB], hi[2 * kB], t2[2 * kB];
+      int q[kB];
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
-        const int j = j0 + b * NT;
-        lo[b] = hi[b] = 0u; t1[b] = t2[b] = tag;
-        if (j < m) { if (ll_gpu_scope) ll_ld4<true>(cells + j, lo[b], t1[b], hi[b], t2[b]); else ll_ld4<false>(cells + j, lo[b], t1[b], hi[b], t2[b]); }
-      }
+        int pos = threadIdx.x + (k0 + b) * NT + r0; if (pos >= span) pos -= span;
+        q[b] = (k0 + b < K && pos < npair) ? pos : -1;
 #pragma unroll
-      for (int b = 0; b < kB; ++b) {
-        const int j = j0 + b * NT;
-        w[b] = 0.0;
-        if (j < m) {
-          if (t1[b] == tag && t2[b] == tag) w[b] = __hiloint2double((int)hi[b], (int)lo[b]);
-          else {  // not there yet: poll (bounded)
-            long long t0 = 0;
-            for (;;) {
-              ll_ld4<false>(cells + j, lo[b], t1[b], hi[b], t2[b]);
-              if (t1[b] == tag && t2[b] == tag) break;
-              if (t0 == 0) t0 = clock64();
-              else if (clock64() - t0 > spin_limit) { atomicExch(errp, 1); break; }
-            }
-            w[b] = __hiloint2double((int)hi[b], (int)lo[b]);
+        for (int e = 0; e < 2; ++e) {
+          lo[2 * b + e] = hi[2 * b + e] = 0u; t1[2 * b + e] = t2[2 * b + e] = tag;
+          if (q[b] >= 0 && 2 * q[b] + e < m) {
+            if (ll_gpu_scope) ll_ld4<true>(cells + 2 * q[b] + e, lo[2 * b + e], t1[2 * b + e], hi[2 * b + e], t2[2 * b + e]);
+            else ll_ld4<false>(cells + 2 * q[b] + e, lo[2 * b + e], t1[2 * b + e], hi[2 * b + e], t2[2 * b + e]);
           }
         }
       }
-    } else {
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
-        const int j = j0 + b * NT;
-        w[b] = (j < m) ? __ldcg(src + j) : 0.0;
+        if (q[b] < 0) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = 2 * q[b] + e, c = 2 * b + e;
+          if (j >= m) continue;
+          if (!(t1[c] == tag && t2[c] == tag)) {  // not there yet: poll (bounded)
+            long long t0 = 0;
+            for (;;) {
+              ll_ld4<false>(cells + j, lo[c], t1[c], hi[c], t2[c]);
+              if (t1[c] == tag && t2[c] == tag) break;
+              if (t0 == 0) t0 = clock64();
+              else if (clock64() - t0 > spin_limit) { atomicExch(errp, 1); break; }
+            }
+          }
+          finish(j, __hiloint2double((int)hi[c], (int)lo[c]));
+        }
       }
     }
+  } else {
+    constexpr int kB = 8;  // 16-byte loads in flight per thread
+    for (int k0 = 0; k0 < K; k0 += kB) {
+      double2 w[kB];
+      int q[kB];
 #pragma unroll
-    for (int b = 0; b < kB; ++b) {
-      const int j = j0 + b * NT;
-      if (j < m) {
-        double v = w[b];
-        if (scale) v = (mode == RS_DIV) ? (w[b] / nrm) : div_by_invariant(w[b], nrm, rinv);
-        vs[j] = v;
-        part += v;
+      for (int b = 0; b < kB; ++b) {
+        int pos = threadIdx.x + (k0 + b) * NT + r0; if (pos >= span) pos -= span;
+        q[b] = (k0 + b < K && pos < npair) ? pos : -1;
+        w[b] = make_double2(0.0, 0.0);
+        if (q[b] >= 0) {
+          if (2 * q[b] + 1 < m) asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(w[b].x), "=d"(w[b].y) : "l"(src + 2 * q[b]) : "memory");
+          else w[b].x = __ldcg(src + 2 * q[b]);   // odd m: never read past the caller's vector
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        if (q[b] < 0) continue;
+        finish(2 * q[b], w[b].x);
+        finish(2 * q[b] + 1, w[b].y);
       }
     }
   }
   if (threadIdx.x == 0) vs[m] = 0.0;  // column of the padding entries
-  return res_block_sum<NT>(part, red_s, fin);  // contains the __syncthreads that publish vs
+  __syncthreads();
+  double part = 0.0;                   // CTA-independent order: thread t adds entries t, t + NT, ...
+  for (int j = threadIdx.x; j < m; j += NT) part += vs[j];
+  return res_block_sum<NT>(part, red_s, fin);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -714,7 +747,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   // ---- phase 0: u = M u0 + u0 (or u0), squared norm (clipper.cpp:193-198) ---------------------
   {
     if (P.rescale_u0) {
-      res_stage<NT, SHARDED>(RS_RAW, m, a.u0, nullptr, 0u, 1.0, vs, red_s, fin, errp, a.spin_limit);
+      res_stage<NT, SHARDED>(RS_RAW, m, a.u0, nullptr, 0u, 1.0, vs, red_s, fin, errp, a.spin_limit, 0, bid * 416);
       RES_LAP(ns_st);
       RES_SWEEP();
     }
@@ -738,7 +771,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   {
     const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
                                                SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
-                                               errp, a.spin_limit, a.ll_gpu_scope);
+                                               errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
     RES_LAP(ns_st);
     RES_SWEEP();
     cur = 1;
@@ -784,7 +817,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         // trial point into shared memory, sweep of the CTA's rows
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
         const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
-                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope);
+                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
         RES_LAP(ns_st);
         RES_SWEEP();
         ++n_evals;
@@ -902,7 +935,7 @@ __global__ void __launch_bounds__(NT, 1) matvec_resident_kernel(ResArgs a, const
     fence_mbar_init();
   }
   __syncthreads();
-  const double sumv = res_stage<NT, false>(RS_RAW, a.m, v, nullptr, 0u, 1.0, vs, red_s, fin, &a.sb->error, a.spin_limit);
+  const double sumv = res_stage<NT, false>(RS_RAW, a.m, v, nullptr, 0u, 1.0, vs, red_s, fin, &a.sb->error, a.spin_limit, 0, bid * 416);
   const bool ptab_sh = (it1 - it0) + (unsigned int)NW <= plan.pieces_cap;
   double* const ptab = ptab_sh ? reinterpret_cast<double*>(smem + plan.off_pieces) : a.pieces + (size_t)bid * NW * kPieceVals;
   const unsigned int isub = ptab_sh ? it0 : 0u;

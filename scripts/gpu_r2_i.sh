@@ -2,6 +2,8 @@
 # 2-GPU A/B of the LL staging load flavour; N=1 bench after the barrier fix
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+export CLP_SKIP_C4=1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_batch.py tests/test_gpu_sharded.py -m gpu -q --maxfail=10 > gpurun_out/pytest_i.log 2>&1; tail -3 gpurun_out/pytest_i.log
 CLP_PROF_CTAS=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-config4 > gpurun_out/benchi.json 2> gpurun_out/benchi.err
 python - <<'PY'
 import json
@@ -9,7 +11,7 @@ d=json.load(open("gpurun_out/benchi.json")); c=d["config"]
 print("N=1", "value %.4g"%d["value"], "ms/step %.3f"%d["ms_per_step"], "solver %.3f"%c["solver_kernel_ms"], {k:round(v,3) for k,v in c["solver_phase_ms"].items()}, "roofline %.3f"%d["roofline"]["frac"])
 PY
 grep "clp prof" gpurun_out/benchi.err | tail -4
-for scope in 1 0; do
+for scope in 1; do
   CLP_LL_GPU_SCOPE=$scope CLP_PROF_CTAS=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29700+scope)) bench.py --gpus 2 --steps 10 --warmup 3 --no-config4 > gpurun_out/benchi_n2_s$scope.json 2> gpurun_out/benchi_n2_s$scope.err
   echo "N=2 gpu_scope=$scope rc=$?"; grep "clp prof" gpurun_out/benchi_n2_s$scope.err | grep "148 CTAs" | tail -4
   python - $scope <<'PY'
