@@ -1516,7 +1516,8 @@ int batch_solve(clp_batch b, int kind, int dd, int32_t nprob, const double* cons
     if (mp <= 0 || mp > kBatchMaxM) return bfail(b, CLP_ERR_INVALID, "batched problems need 1 <= m <= 4096 associations");
     q.d1_off = nd1; q.d2_off = nd2; q.a_off = a2a ? -1 : na; q.u_off = nu;
     q.n1 = (int)n1[p]; q.n2 = (int)n2[p]; q.m = (int)mp; q.pad_ = 0;
-    nd1 += (long long)dd * n1[p]; nd2 += (long long)dd * n2[p]; if (!a2a) na += 2 * mp; nu += mp;
+    nd1 += (long long)dd * n1[p]; nd2 += (long long)dd * n2[p]; if (!a2a) na += 2 * mp;
+    nu += (mp + 1) & ~1LL;  // every problem's u0 / u slot starts on a 16-byte boundary (the kernels use 16-byte loads)
     max_m = std::max(max_m, (int)mp);
   }
   const size_t bytes_in = (size_t)(nd1 + nd2 + nu) * 8 + (size_t)na * 4 + (size_t)nprob * sizeof(BatchProblem);

@@ -593,7 +593,7 @@ __device__ __forceinline__ double staged_value(const StageArgs& s, int j, double
   if (s.mode == STAGE_DIV) return ll_load(s.llA + j, s.tag, s.error) / nrm;
   double w = __dadd_rn(s.srcA[j], __dmul_rn(s.alpha, ll_load(s.llB + j, s.tag, s.error)));
   w = (w < 0.0) ? 0.0 : w;
-  return (s.z > 0.0) ? w / nrm : w;
+  return (s.z > 0.0 && w != 0.0) ? w / nrm : w;  // 0 / nrm == 0: skip the division's special-case path
 }
 
 // Stage columns [seg*W, seg*W+W) of v into shared memory (zero beyond m).  If `owner`, also
@@ -641,7 +641,7 @@ __device__ void stage_segment(const StageArgs& s, const Plan& p, int m, int seg,
           else {
             double w = __dadd_rn(ua[b], __dmul_rn(s.alpha, x));
             w = (w < 0.0) ? 0.0 : w;
-            v[b] = (s.z > 0.0) ? w / nrm : w;
+            v[b] = (s.z > 0.0 && w != 0.0) ? w / nrm : w;  // most entries are exactly 0: skip the division's slow special-case path
           }
         }
       }
