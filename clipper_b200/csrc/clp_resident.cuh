@@ -733,7 +733,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   unsigned long long round = 0, seq = a.seq0;
   unsigned int ctag = 0u;  // tag under which the candidates of parity cpar were written
   unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, ns_st = 0, tmark = global_ns();
-#define RES_LAP(acc) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; }
+#define RES_LAP(acc) { if (threadIdx.x == 0) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; } }
 #define RES_ZERO() _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
 #define RES_FOR_ROWS(i, itx, sx)                                                                    \
   for (int t_ = threadIdx.x, i = 0, sx = 0, w0_ = 0, w1_ = 0; t_ < nrow; t_ += NT)                  \
