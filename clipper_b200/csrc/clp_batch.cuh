@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
       a.out = ba.out + p;
       a.rank = 0; a.world = 1;
       for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = nullptr; a.peer_comm[r] = nullptr; }
-      a.comm = nullptr; a.seq0 = 0; a.spin_limit = ba.spin_limit; a.ll_gpu_scope = 0; a.ring_stages = 0; a.pieces_cap = 0u; a.state_cap = 0u; a.redll = nullptr; a.prof_cta = nullptr;
+      a.comm = nullptr; a.seq0 = 0; a.spin_limit = ba.spin_limit; a.ll_gpu_scope = 0; a.ring_stages = 0; a.pieces_cap = 0u; a.state_cap = 0u; a.redll = nullptr; a.prof_cta = nullptr; a.prof_laps = 0;
       sa = a;
     }
     __syncthreads();

@@ -404,6 +404,7 @@ ResArgs res_args(clp_handle h) {
   res_pick_caps(h, h->res_cfg_eff, &a.pieces_cap, &a.state_cap);
   a.redll = h->res_redll.as<uint4>();
   a.prof_cta = h->prof_ctas ? h->prof_buf.as<double>() : nullptr;
+  a.prof_laps = (h->prof_ctas || env_int("CLP_PROF_LAPS", 1)) ? 1 : 0;
   return a;
 }
 

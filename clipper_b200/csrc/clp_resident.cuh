@@ -63,7 +63,8 @@ struct ResArgs {
   int ring_stages;         // > 0: cp.async.bulk ring with this many stages per warp (RING instances)
   unsigned int pieces_cap, state_cap;  // on-chip piece table (entries) / row state (rows) per CTA, 0: keep them in HBM
   uint4* redll;            // [2][G][8] per-CTA partial sums as self-validating LL cells (zeroed before the launch)
-  double* prof_cta;        // nullable: [G][4] per-CTA phase times in ns (sweeps, epilogues, exchanges) -- diagnostics
+  double* prof_cta;        // nullable: [G][4] per-CTA phase times in ns (sweeps, epilogues, exchanges, staging) -- diagnostics
+  int prof_laps;           // thread 0 of every CTA reads %globaltimer four times per evaluation (phase split in clp_solution)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -733,7 +734,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   unsigned long long round = 0, seq = a.seq0;
   unsigned int ctag = 0u;  // tag under which the candidates of parity cpar were written
   unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, ns_st = 0, tmark = global_ns();
-#define RES_LAP(acc) { if (threadIdx.x == 0) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; } }
+#define RES_LAP(acc) { if (a.prof_laps && threadIdx.x == 0) { const unsigned long long t_ = global_ns(); acc += t_ - tmark; tmark = t_; } }
 #define RES_ZERO() _Pragma("unroll") for (int q_ = 0; q_ < kRedVals; ++q_) loc[q_] = 0.0;
 #define RES_FOR_ROWS(i, itx, sx)                                                                    \
   for (int t_ = threadIdx.x, i = 0, sx = 0, w0_ = 0, w1_ = 0; t_ < nrow; t_ += NT)                  \
