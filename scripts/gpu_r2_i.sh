@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export CLP_SKIP_C4=1
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_batch.py tests/test_gpu_sharded.py -m gpu -q --maxfail=10 > gpurun_out/pytest_i.log 2>&1; tail -3 gpurun_out/pytest_i.log
+timeout 900 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_fullsize.py -m gpu -q --maxfail=10 > gpurun_out/pytest_i.log 2>&1; tail -3 gpurun_out/pytest_i.log
 CLP_PROF_CTAS=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-config4 > gpurun_out/benchi.json 2> gpurun_out/benchi.err
 python - <<'PY'
 import json
