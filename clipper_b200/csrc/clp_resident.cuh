@@ -206,18 +206,6 @@ __device__ __forceinline__ void ll_ld4(const uint4* p, unsigned int& lo, unsigne
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
 }
 
-__device__ __forceinline__ double ll_load_bounded(const uint4* p, unsigned int tag, int* errp, long long spin_limit) {
-  unsigned int lo, t1, hi, t2;
-  long long t0 = 0;
-  for (;;) {
-    ll_ld4<false>(p, lo, t1, hi, t2);
-    if (t1 == tag && t2 == tag) break;
-    if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > spin_limit) { atomicExch(errp, 1); break; }
-  }
-  return __hiloint2double((int)hi, (int)lo);
-}
-
 template <int NT, bool SHARDED>
 __device__ double res_stage(int mode, int m, const double* src, const uint4* cells, unsigned int tag, double z,
                             double* vs, double* red_s, double* fin, int* errp, long long spin_limit, int ll_gpu_scope = 0,
@@ -730,25 +718,12 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   // candidate trial points: parity par, kind 0 = "accept" (max(v + gradFnew, 0)), 1 = "reject" (max(u + alpha beta gradF, 0))
   auto cand_store = [&](int par, int kind, int i, double v, unsigned int tag) {
     const size_t off = (size_t)(par * 2 + kind) * mp + i;
-    a.cand[off] = v;  // local copy: plain (published to the other CTAs by the exchange's release / acquire)
     if constexpr (SHARDED) {
+      ll_store(a.ll + off, v, tag);
       for (int r = 0; r < a.world; ++r)
-        if (r != a.rank) ll_store(a.peer_ll[r] + off, v, tag);  // peers' replicas: self-validating LL cells over NVLink
-    }
-  };
-  // Sharded: the entries of the REMOTE rows arrive in this rank's LL block.  Instead of letting every CTA validate all
-  // m cells when it stages the next trial vector (16 B per entry, measured 11 us per evaluation), every CTA unpacks a
-  // 1/G slice of them into the plain candidate arrays right before it publishes its partial sums -- the exchange's
-  // release / acquire then covers them like the local rows, and staging is the same 8-byte path as on one GPU.
-  auto unpack_remote = [&](int par, int nkinds, unsigned int tag) {
-    if constexpr (SHARDED) {
-      const int nrem = m - a.rows;  // remote rows: [0, row0) and [row0 + rows, m)
-      for (int g = bid * NT + (int)threadIdx.x; g < nkinds * nrem; g += a.G * NT) {
-        const int kind = g / nrem, r = g - kind * nrem;
-        const int i = r < a.row0 ? r : r + a.rows;
-        const size_t off = (size_t)(par * 2 + kind) * mp + i;
-        a.cand[off] = ll_load_bounded(a.ll + off, tag, errp, a.spin_limit);
-      }
+        if (r != a.rank) ll_store(a.peer_ll[r] + off, v, tag);
+    } else {
+      a.cand[off] = v;
     }
   };
 
@@ -793,15 +768,15 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
       cand_store(cpar ^ 1, 0, i, t, tag);
       loc[0] += t * t;
     }
-    unpack_remote(cpar ^ 1, 1, tag);
     RES_EXCHANGE();
     cpar ^= 1; ctag = tag;
     z = vals[0];
   }
   // ---- phase 1: u /= |u|; Mhat u, Chat u; initial d (clipper.cpp:198-209) ----------------------
   {
-    const double sumu = res_stage<NT, false>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp, nullptr, ctag, z, vs, red_s, fin,
-                                             errp, a.spin_limit, 0, bid * 416);
+    const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
+                                               SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
+                                               errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
     RES_LAP(ns_st);
     RES_SWEEP();
     cur = 1;
@@ -834,7 +809,6 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         loc[1] += w * w;
         cand_store(cpar ^ 1, 0, i, w, tag);
       }
-      unpack_remote(cpar ^ 1, 1, tag);
       RES_EXCHANGE();
       cpar ^= 1; ctag = tag;
       F = vals[0]; z = vals[1];
@@ -847,8 +821,8 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
       for (int k = 0; k < P.maxlsiters; ++k) {
         // trial point into shared memory, sweep of the CTA's rows
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
-        const double sumv = res_stage<NT, false>(RS_STEP, m, a.cand + coff, nullptr, ctag, z,
-                                                 vs, red_s, fin, errp, a.spin_limit, 0, bid * 416);
+        const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
+                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
         RES_LAP(ns_st);
         RES_SWEEP();
         ++n_evals;
@@ -873,7 +847,6 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
           cand_store(cpar ^ 1, 0, i, wb_, tag);
           cand_store(cpar ^ 1, 1, i, wa, tag);
         }
-        unpack_remote(cpar ^ 1, 2, tag);
         RES_EXCHANGE();
         cpar ^= 1; ctag = tag;
         // the line-search decision (clipper.cpp:242-251), identical on every CTA / rank
