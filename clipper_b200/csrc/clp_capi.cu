@@ -523,10 +523,11 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   // byte-balanced contiguous item range of every CTA (depends on the grid size: rebuilt with the plan)
   int G = p.G;
   if (resident) {
-    // one fat CTA per SM; small problems use fewer CTAs -- every CTA should stream at least ~96 KB per sweep (about
-    // 2 us), below that the device-wide exchange costs more than the extra SMs save; shards sharing a GPU honour the cap
+    // one fat CTA per SM; small problems use fewer CTAs -- every CTA should stream at least ~32 KB per sweep (measured
+    // at m = 1000, 360 KB per sweep: 28.6 / 13.0 / 9.0 / 8.5 / 19.7 us per evaluation with 1 / 4 / 8 / 32 / 125 CTAs);
+    // shards sharing a GPU honour the cap
     h->res_NI = NI;
-    const long long by_bytes = (long long)((double)h->sp_nnz * (sizeof(T) + 2.0) / (96.0 * 1024.0));
+    const long long by_bytes = (long long)((double)h->sp_nnz * (sizeof(T) + 2.0) / (32.0 * 1024.0));
     G = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(h->grid_cap > 0 ? std::min(h->grid_cap, h->sm_count) : h->sm_count, NI / 2),
                                                         std::max<long long>(1, by_bytes)));
     if (env_int("CLP_RES_G", 0) > 0) G = std::max(1, std::min(env_int("CLP_RES_G", 0), std::min(h->sm_count, std::max(1, NI / 2))));
