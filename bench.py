@@ -205,7 +205,10 @@ def run_ours(args):
         clip.set_dense_mode(int(os.environ["CLP_DENSE_MODE"]))
     if os.environ.get("CLP_CTAS_PER_SM"):
         _capi.check(h, L.clp_set_ctas_per_sm(h, int(os.environ["CLP_CTAS_PER_SM"])))
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the library: the legacy default stream has handle 0, which
+    # clp_set_stream reads as "create your own" -- the CUDA events below must sit on the stream the kernels run on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     clip.set_stream(stream.cuda_stream)
 
     # ---- inputs resident in HBM

@@ -278,6 +278,9 @@ def run_bench(args, METRIC, UNIT):
 
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
+    # torch and the library share one real stream: the legacy default stream's handle is 0, which clp_set_stream reads
+    # as "create your own", and the timing events must sit on the stream the kernels run on
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 
     def one_workload(name, m_override, steps, warmup):
         prob = datagen.config_problem(name, m_override)
@@ -294,7 +297,7 @@ def run_bench(args, METRIC, UNIT):
             clip.set_dense_mode(int(os.environ["CLP_DENSE_MODE"]))
         if os.environ.get("CLP_CTAS_PER_SM"):
             _capi.check(clip.handle, _capi.load().clp_set_ctas_per_sm(clip.handle, int(os.environ["CLP_CTAS_PER_SM"])))
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream()   # run_bench installed a non-default stream (handle != 0)
         clip.set_stream(stream.cuda_stream)
         D1 = torch.from_numpy(np.ascontiguousarray(prob["D1"].T)).to(dev)
         D2 = torch.from_numpy(np.ascontiguousarray(prob["D2"].T)).to(dev)
