@@ -341,7 +341,6 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
       a.u0 = ba.u0 + P.u_off;
       a.vecs = reinterpret_cast<double*>(sc + L.vecs);
       a.cand = reinterpret_cast<double*>(sc + L.cand);
-      a.flags = nullptr;
       a.ll = nullptr;
       a.mpad = (long long)ld;
       a.pieces = reinterpret_cast<double*>(sc + L.pieces);

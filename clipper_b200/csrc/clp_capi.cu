@@ -389,7 +389,6 @@ ResArgs res_args(clp_handle h) {
   a.u0 = h->u0dev.as<double>();
   a.vecs = h->res_vecs.as<double>();
   a.cand = h->res_cand.as<double>();
-  a.flags = (h->world == 1 && env_int("CLP_STAGE_FLAGS", 1)) ? reinterpret_cast<unsigned char*>(a.cand + (size_t)4 * h->mpad) : nullptr;
   a.ll = h->llbuf.as<uint4>();
   a.mpad = h->mpad;
   a.pieces = h->res_pieces.as<double>();
@@ -537,7 +536,7 @@ int build_sparse(clp_handle h, bool force, bool resident) {
     CLP_CUDA(h, res_set_attrs<T>(h, h->res_cfg_eff, h->world > 1));
     const int NW = kResCfgs[h->res_cfg_eff].NT / 32;
     CLP_CUDA(h, h->res_vecs.ensure((size_t)R_SLOTS * h->mpad * sizeof(double)));
-    CLP_CUDA(h, h->res_cand.ensure((size_t)4 * h->mpad * (sizeof(double) + 1)));  // candidate points + their non-zero flags
+    CLP_CUDA(h, h->res_cand.ensure((size_t)4 * h->mpad * sizeof(double)));
     CLP_CUDA(h, h->res_pieces.ensure(((size_t)NI + (size_t)G * NW + 8) * kPieceVals * sizeof(double)));
     CLP_CUDA(h, h->res_redll.ensure((size_t)2 * G * kRedVals * sizeof(uint4)));
   }

@@ -47,7 +47,6 @@ struct ResArgs {
   const double* u0;        // [m]
   double* vecs;            // R_SLOTS plain vectors x mpad (only the entries of the local rows are ever touched)
   double* cand;            // world == 1: candidate trial points, [2 parities][2: accept, reject][mpad] doubles
-  unsigned char* flags;    // world == 1, nullable: [2][2][mpad] "entry is not +0.0" -- lets the staging skip the zeros
   uint4* ll;               // world  > 1: the same as LL cells + one more vector (final iterate): [5][mpad], replicated
   long long mpad;
   double* pieces;          // [(NI + G * warps)][8]
@@ -210,7 +209,7 @@ __device__ __forceinline__ void ll_ld4(const uint4* p, unsigned int& lo, unsigne
 template <int NT, bool SHARDED>
 __device__ double res_stage(int mode, int m, const double* src, const uint4* cells, unsigned int tag, double z,
                             double* vs, double* red_s, double* fin, int* errp, long long spin_limit, int ll_gpu_scope = 0,
-                            int rot = 0, const unsigned char* flags = nullptr) {
+                            int rot = 0) {
   // Every CTA of the grid reads the SAME m values at the same moment.  Measured on B200 (profiles/r02i): with all 148
   // CTAs walking the vector in the same order, four 8-byte loads in flight per thread, this step took 14.7 us per
   // evaluation at m = 20 000 -- a fifth of the solver -- while the sweep itself ran at the HBM peak.  So: 16-byte
@@ -230,31 +229,7 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
       vs[j] = v;
     }
   };
-  if (!SHARDED && mode != RS_RAW && flags != nullptr) {
-    // A projected iterate is mostly exact zeros (95 % at config 2 after the first iterations): the row owners also
-    // store one byte per entry ("is not +0.0"); 16 flags per 16-byte load, and only the flagged values are fetched
-    // -- 1/6 of the bytes when the vector is sparse, the same bytes + 12 % when it is dense (first evaluations).
-    const int ngroup = (m + 15) >> 4;
-    const int KG = (ngroup + NT - 1) / NT;
-    const int gspan = KG * NT;
-    const int g0 = ((rot % gspan) + gspan) % gspan & ~31;
-    for (int k = 0; k < KG; ++k) {
-      int g = threadIdx.x + k * NT + g0; if (g >= gspan) g -= gspan;
-      if (g >= ngroup) continue;
-      uint4 f;
-      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(f.x), "=r"(f.y), "=r"(f.z), "=r"(f.w) : "l"(flags + 16 * g) : "memory");
-      const unsigned int fw[4] = {f.x, f.y, f.z, f.w};
-      double w[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = 16 * g + e;
-        w[e] = 0.0;
-        if (((fw[e >> 2] >> (8 * (e & 3))) & 0xffu) != 0u && j < m) w[e] = __ldcg(src + j);
-      }
-#pragma unroll
-      for (int e = 0; e < 16; ++e) finish(16 * g + e, w[e]);
-    }
-  } else if (SHARDED && mode != RS_RAW) {
+  if (SHARDED && mode != RS_RAW) {
     constexpr int kB = 4;  // pairs (= 2 LL cells each) in flight per thread
     for (int k0 = 0; k0 < K; k0 += kB) {
       unsigned int lo[2 * kB], t1[2 * kB], hi[2 * kB], t2[2 * kB];
@@ -293,7 +268,9 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
       }
     }
   } else {
-    constexpr int kB = 8;  // 16-byte loads in flight per thread
+    constexpr int kB = 14;  // 16-byte loads in flight per thread: one round trip for m <= 21 504 with 768 threads (the
+                            // step is latency-bound: fetching only the non-zero entries through a flag byte per entry moved
+                            // 1/6 of the bytes but added a dependent round trip and was slower, 14.4 vs 7.9 us per evaluation)
     for (int k0 = 0; k0 < K; k0 += kB) {
       double2 w[kB];
       int q[kB];
@@ -749,7 +726,6 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         if (r != a.rank) ll_store(a.peer_ll[r] + off, v, tag);
     } else {
       a.cand[off] = v;
-      if (a.flags) a.flags[off] = (__double_as_longlong(v) != 0LL) ? 1 : 0;
     }
   };
 
@@ -802,8 +778,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   {
     const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
                                                SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
-                                               errp, a.spin_limit, a.ll_gpu_scope, bid * 416,
-                                               a.flags ? a.flags + (size_t)(cpar * 2) * mp : nullptr);
+                                               errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
     RES_LAP(ns_st);
     RES_SWEEP();
     cur = 1;
@@ -849,8 +824,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         // trial point into shared memory, sweep of the CTA's rows
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
         const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
-                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope, bid * 416,
-                                                   a.flags ? a.flags + coff : nullptr);
+                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
         RES_LAP(ns_st);
         RES_SWEEP();
         ++n_evals;
