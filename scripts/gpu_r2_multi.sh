@@ -8,8 +8,10 @@ export CLP_SKIP_C4=1
 timeout 600 python -m pytest tests/test_gpu_sharded.py "tests/test_gpu_parity.py::test_error_behaviour" -m gpu -q > gpurun_out/pytest_multi.log 2>&1; tail -3 gpurun_out/pytest_multi.log
 for N in 2 4 8; do
   if [ $N -le $NG ]; then
+    if [ $N -eq $NG ] || [ "$CHECK_ALL" = "1" ]; then
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) scripts/check_sharded.py 3000 20000 > gpurun_out/check_sharded_n$N.log 2>&1
     echo "check N=$N rc=$?"; grep '^{' gpurun_out/check_sharded_n$N.log | tail -2; grep -i "error\|Traceback" gpurun_out/check_sharded_n$N.log | head -5
+    fi
     CLP_PROF_CTAS=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
     echo "bench N=$N rc=$?"; grep "clp prof" gpurun_out/bench_n$N.err | grep "148 CTAs" | tail -4
     python - $N <<'PY'
