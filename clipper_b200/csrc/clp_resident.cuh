@@ -230,7 +230,8 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
     }
   };
   if (SHARDED && mode != RS_RAW) {
-    constexpr int kB = 7;  // pairs (= 2 LL cells each) in flight per thread: two round trips at m = 20 000
+    constexpr int kB = 4;  // pairs (= 2 LL cells each) in flight per thread (7 made the sharded instance spill inside the
+                           // sweep: N = 2 solver 6.8 -> 9.8 ms, staging unchanged at 11 us)
     for (int k0 = 0; k0 < K; k0 += kB) {
       unsigned int lo[2 * kB], t1[2 * kB], hi[2 * kB], t2[2 * kB];
       int q[kB];
