@@ -269,9 +269,9 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
       }
     }
   } else {
-    constexpr int kB = 14;  // 16-byte loads in flight per thread: one round trip for m <= 21 504 with 768 threads (the
-                            // step is latency-bound: fetching only the non-zero entries through a flag byte per entry moved
-                            // 1/6 of the bytes but added a dependent round trip and was slower, 14.4 vs 7.9 us per evaluation)
+    constexpr int kB = 8;  // 16-byte loads in flight per thread (14 = one round trip at m = 20 000 raised the kernel's stack frame
+                           // to 336 bytes: spills; fetching only the non-zero entries through a flag byte per entry moved 1/6 of
+                           // the bytes but added a dependent round trip and was slower: 14.4 vs 7.9 us per evaluation)
     for (int k0 = 0; k0 < K; k0 += kB) {
       double2 w[kB];
       int q[kB];
