@@ -6,25 +6,11 @@ rm -f gpurun_out/fullsize_parity.jsonl
 timeout 2400 python -m pytest tests -m gpu -q --maxfail=10 --durations=8 > gpurun_out/pytest_j.log 2>&1
 echo "pytest(j) rc=$?" >> gpurun_out/pytest_j.log
 tail -16 gpurun_out/pytest_j.log
-cat > /tmp/c1_once.py <<'PY'
-import numpy as np, clipper_b200 as clp
-from clipper_b200 import datagen
-import sys
-prob=datagen.config_problem("c1"); cfg=prob["cfg"]
-ip=clp.invariants.EuclideanDistanceParams(); ip.sigma,ip.epsilon=cfg["sigma"],cfg["epsilon"]
-c=clp.CLIPPER(clp.invariants.EuclideanDistance(ip),clp.Params())
-if len(sys.argv)>1: c.set_dense_mode(int(sys.argv[1]))
-c.score_pairwise_consistency(prob["D1"],prob["D2"],prob["A"]); c.solve(prob["u0"])
-s=c.get_solution(); print("c1 mode",c.dense_mode(),"F",s.score,"nodes",len(s.nodes),"evals",s.n_evals)
-b=clp.BatchCLIPPER(clp.invariants.EuclideanDistance(ip),clp.Params())
-sols=b.solve_many([dict(D1=prob["D1"],D2=prob["D2"],A=prob["A"],u0=prob["u0"])]*3)
-print("batch F",[x.score for x in sols])
-PY
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/c1_once.py > gpurun_out/sanitizer_${tool}_c1.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_c1.py > gpurun_out/sanitizer_${tool}_c1.log 2>&1
   echo "sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|c1 mode|batch F" gpurun_out/sanitizer_${tool}_c1.log | tail -4
 done
-timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python /tmp/c1_once.py 3 > gpurun_out/sanitizer_memcheck_c1_mode3.log 2>&1; grep -E "ERROR SUMMARY|c1 mode" gpurun_out/sanitizer_memcheck_c1_mode3.log | tail -2
+timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_c1.py 3 > gpurun_out/sanitizer_memcheck_c1_mode3.log 2>&1; grep -E "ERROR SUMMARY|c1 mode" gpurun_out/sanitizer_memcheck_c1_mode3.log | tail -2
 for cfg in 1 0 4 5 6; do
   CLP_RES_CFG=$cfg python - <<'PY'
 import os, numpy as np, clipper_b200 as clp, ctypes as C, torch
