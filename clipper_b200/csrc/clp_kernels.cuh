@@ -8,6 +8,10 @@
 //   K3-K5 solver_kernel       whole findDenseClique() as ONE persistent cooperative kernel:
 //                             step/projection, objective, backtracking line search, penalty
 //                             ramp, all decided on the device            (ref clipper.cpp:172-283)
+//                             -- the segmented solver (any m, dense sweeps).  The default for m <= 27648 is
+//                             solver_resident_kernel in clp_resident.cuh (whole trial vector in shared memory, one
+//                             device-wide synchronisation per evaluation); clp_batch.cuh runs that solver body with
+//                             one CTA per problem for batches of small problems
 //   K7  encode/decode kernels  get/setMatrixData                        (ref clipper.cpp:131-166)
 //
 // Data layout in HBM.  The affinity matrix is DENSE and symmetric, row-major with a leading
