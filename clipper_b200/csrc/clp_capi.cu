@@ -542,7 +542,8 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   }
   CLP_CUDA(h, h->sp_part.ensure(2 * ((size_t)G + 1) * sizeof(unsigned int)));
   sparse_partition_kernel<<<(G + 1 + 255) / 256, 256, 0, h->stream>>>(h->sp.itemptr, h->rows_pad, nseg, G, h->sp_part.as<unsigned int>(),
-                                                                      h->sp_part.as<unsigned int>() + G + 1);
+                                                                      h->sp_part.as<unsigned int>() + G + 1,
+                                                                      (unsigned int)env_int("CLP_ITEM_COST", (int)kItemCost));
   CLP_CUDA(h, cudaGetLastError());
   h->sp.cta_first = h->sp_part.as<unsigned int>();
   h->sp.cta_chunk = h->sp.cta_first + G + 1;
@@ -860,7 +861,7 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   CLP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   cudaError_t le;
   if (h->dense_mode_eff == 6) {
-    if (h->prof_ctas) CLP_CUDA(h, h->prof_buf.ensure((size_t)h->res_G * 4 * sizeof(double)));
+    if (h->prof_ctas) CLP_CUDA(h, h->prof_buf.ensure((size_t)h->res_G * 8 * sizeof(double)));
     // the per-CTA partial sums travel as LL cells tagged with the launch-local round number: start from tag 0
     CLP_CUDA(h, cudaMemsetAsync(h->res_redll.p, 0, (size_t)2 * h->res_G * kRedVals * sizeof(uint4), h->stream));
     ResArgs ra = res_args(h);
@@ -882,12 +883,17 @@ int solve_core(clp_handle h, clp_solution* out, double* u_out_host, double* u_ou
   const SolverOut so = *reinterpret_cast<const SolverOut*>(h->pinned);
   h->seq = so.seq_end;
   if (h->prof_ctas && h->dense_mode_eff == 6) {  // diagnostics: spread of the per-CTA phase times
-    std::vector<double> pc((size_t)h->res_G * 4);
+    std::vector<double> pc((size_t)h->res_G * 8);
     CLP_CUDA(h, cudaMemcpy(pc.data(), h->prof_buf.p, pc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h->prof_ctas >= 2) {  // one line per CTA: index, ms in sweeps / epilogues / exchanges / staging, items, chunks
+      for (int b = 0; b < h->res_G; ++b)
+        std::fprintf(stderr, "[clp cta] %d %.4f %.4f %.4f %.4f %.0f %.0f\n", b, 1e-6 * pc[(size_t)b * 8], 1e-6 * pc[(size_t)b * 8 + 1],
+                     1e-6 * pc[(size_t)b * 8 + 2], 1e-6 * pc[(size_t)b * 8 + 3], pc[(size_t)b * 8 + 4], pc[(size_t)b * 8 + 5]);
+    }
     const char* nm[4] = {"sweeps", "epilogues", "exchanges", "staging"};
     for (int q = 0; q < 4; ++q) {
       double lo = 1e300, hi = 0, sum = 0;
-      for (int b = 0; b < h->res_G; ++b) { const double x = pc[(size_t)b * 4 + q]; lo = std::min(lo, x); hi = std::max(hi, x); sum += x; }
+      for (int b = 0; b < h->res_G; ++b) { const double x = pc[(size_t)b * 8 + q]; lo = std::min(lo, x); hi = std::max(hi, x); sum += x; }
       std::fprintf(stderr, "[clp prof] %-9s per solve: min %.3f  mean %.3f  max %.3f ms over %d CTAs (%lld evaluations)\n", nm[q],
                    1e-6 * lo, 1e-6 * sum / h->res_G, 1e-6 * hi, h->res_G, (long long)so.n_evals);
     }

@@ -63,7 +63,7 @@ struct ResArgs {
   int ring_stages;         // > 0: cp.async.bulk ring with this many stages per warp (RING instances)
   unsigned int pieces_cap, state_cap;  // on-chip piece table (entries) / row state (rows) per CTA, 0: keep them in HBM
   uint4* redll;            // [2][G][8] per-CTA partial sums as self-validating LL cells (zeroed before the launch)
-  double* prof_cta;        // nullable: [G][4] per-CTA phase times in ns (sweeps, epilogues, exchanges, staging) -- diagnostics
+  double* prof_cta;        // nullable: [G][8] per-CTA phase times in ns (sweeps, epilogues, exchanges, staging), items, chunks
   int prof_laps;           // thread 0 of every CTA reads %globaltimer four times per evaluation (phase split in clp_solution)
 };
 
@@ -899,8 +899,10 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
 
 finish:
   if (a.prof_cta && threadIdx.x == 0) {
-    a.prof_cta[(size_t)bid * 4 + 0] = (double)ns_mv; a.prof_cta[(size_t)bid * 4 + 1] = (double)ns_cb;
-    a.prof_cta[(size_t)bid * 4 + 2] = (double)ns_ex; a.prof_cta[(size_t)bid * 4 + 3] = (double)ns_st;
+    a.prof_cta[(size_t)bid * 8 + 0] = (double)ns_mv; a.prof_cta[(size_t)bid * 8 + 1] = (double)ns_cb;
+    a.prof_cta[(size_t)bid * 8 + 2] = (double)ns_ex; a.prof_cta[(size_t)bid * 8 + 3] = (double)ns_st;
+    a.prof_cta[(size_t)bid * 8 + 4] = (double)(it1 - it0);
+    a.prof_cta[(size_t)bid * 8 + 5] = (double)(a.sp.itemptr[it1] - a.sp.itemptr[it0]);
   }
   if (bid == 0 && threadIdx.x == 0) {
     if (*reinterpret_cast<volatile int*>(errp) != 0) status = 5;

@@ -466,29 +466,30 @@ __device__ __forceinline__ void sell_apply_round(const Entry4<T> (&E)[kSellUnrol
 // (chunks + kItemCost per item), found by bisection on itemptr; inside a CTA the warps draw items from a
 // shared-memory counter.  (Dealing 32-row tiles round-robin, as the dense sweep does, left the slowest CTA
 // with 1.23x the mean bytes at config 2.)
-__device__ __forceinline__ unsigned long long sparse_item_cost(const unsigned int* itemptr, int NI, int nseg, unsigned int g) {
+__device__ __forceinline__ unsigned long long sparse_item_cost(const unsigned int* itemptr, int NI, int nseg, unsigned int g,
+                                                              unsigned int item_cost = kItemCost) {
   const unsigned int seg = g / (unsigned int)NI, it = g - seg * (unsigned int)NI;
   const unsigned int at = (seg >= (unsigned int)nseg) ? itemptr[(size_t)(nseg - 1) * (NI + 1) + NI]
                                                       : itemptr[(size_t)seg * (NI + 1) + it];
-  return (unsigned long long)at + (unsigned long long)kItemCost * g;
+  return (unsigned long long)at + (unsigned long long)item_cost * g;
 }
 
 __global__ void sparse_partition_kernel(const unsigned int* itemptr, int rows_pad, int nseg, int G, unsigned int* cta_first,
-                                        unsigned int* cta_chunk) {
+                                        unsigned int* cta_chunk, unsigned int item_cost) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > G) return;
   const int NI = rows_pad >> 2;
   const unsigned int N = (unsigned int)nseg * (unsigned int)NI;
-  const unsigned long long total = sparse_item_cost(itemptr, NI, nseg, N);
+  const unsigned long long total = sparse_item_cost(itemptr, NI, nseg, N, item_cost);
   const unsigned long long target = total * (unsigned long long)b / (unsigned long long)G;  // total < 2^34, b <= 444
   unsigned int lo = 0, hi = N;  // smallest g with cost(g) >= target
   while (lo < hi) {
     const unsigned int mid = lo + ((hi - lo) >> 1);
-    if (sparse_item_cost(itemptr, NI, nseg, mid) >= target) hi = mid; else lo = mid + 1;
+    if (sparse_item_cost(itemptr, NI, nseg, mid, item_cost) >= target) hi = mid; else lo = mid + 1;
   }
   if (b == G) lo = N;
   cta_first[b] = lo;
-  cta_chunk[b] = (unsigned int)(sparse_item_cost(itemptr, NI, nseg, lo) - (unsigned long long)kItemCost * lo);
+  cta_chunk[b] = (unsigned int)(sparse_item_cost(itemptr, NI, nseg, lo, item_cost) - (unsigned long long)item_cost * lo);
 }
 
 // asks L2 to fetch [p, p + bytes) -- p 16-byte aligned, bytes a non-zero multiple of 16
