@@ -33,7 +33,9 @@ namespace clp {
 
 constexpr unsigned int kZeroSlot = kSegMax * 8;  // byte offset of the zero element behind the staged segment
 constexpr int kSellUnroll = 3;                   // chunks per lane and round; two rounds are in flight
-constexpr unsigned int kItemCost = 16;           // fixed cost of an item (pointer fetch, reduction, store) in chunks
+constexpr unsigned int kItemCost = 128;          // fixed cost of an item (pointer fetch, pipeline restart, reduction, store) in chunks;
+                                                 // measured at m = 80 000 (items of ~430 chunks): 16 -> 0.53, 64 -> 0.75, 128 -> 0.87,
+                                                 // 256 -> 0.80 of the HBM peak in the solver; irrelevant for the whole-row layout
 
 struct SparseView {
   const void* val;               // T [4 * chunks]
