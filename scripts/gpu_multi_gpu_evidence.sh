@@ -6,7 +6,7 @@ NG=$(nvidia-smi -L | wc -l)
 echo "GPUs: $NG"
 export CLP_SKIP_C4=1
 timeout 600 python -m pytest tests/test_gpu_sharded.py "tests/test_gpu_parity.py::test_error_behaviour" -m gpu -q > gpurun_out/pytest_multi.log 2>&1; tail -3 gpurun_out/pytest_multi.log
-for N in 2 4 8; do
+for N in ${NLIST:-2 4 8}; do
   if [ $N -le $NG ]; then
     if [ $N -eq $NG ] || [ "$CHECK_ALL" = "1" ]; then
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) scripts/check_sharded.py 3000 20000 > gpurun_out/check_sharded_n$N.log 2>&1
