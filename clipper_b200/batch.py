@@ -17,14 +17,14 @@ class BatchCLIPPER:
     """invariant: EuclideanDistance (data 2 x n or 3 x n) or PointNormalDistance (6 x n); params: Params (rounding NONZERO or DSD_HEU)"""
 
     def __init__(self, invariant, params=None, device=0):
+        if not isinstance(invariant, (EuclideanDistance, PointNormalDistance)):
+            raise TypeError("a batch scores with the built-in invariants (EuclideanDistance, PointNormalDistance)")
         self._lib = _capi.load()
         self._b = C.c_void_p()
         rc = self._lib.clp_batch_create(int(device), C.byref(self._b))
         if rc != _capi.OK:
             msg = self._lib.clp_batch_last_error(None)
             raise _capi.ClipperError(rc, msg.decode() if msg else "clp_batch_create failed")
-        if not isinstance(invariant, (EuclideanDistance, PointNormalDistance)):
-            raise TypeError("a batch scores with the built-in invariants (EuclideanDistance, PointNormalDistance)")
         self._invariant = invariant
         self._params = params if params is not None else Params()
 

@@ -8,6 +8,7 @@
 #include "../../include/clipper_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -97,6 +98,10 @@ struct clp_handle_s {
   int res_smem_extra = env_int("CLP_RES_SMEM_EXTRA", 1);  // 0: launch with the plan's minimum (piece table / row state in HBM)
   int prof_ctas = env_int("CLP_PROF_CTAS", 0);      // print the per-CTA phase times of every resident solve (stderr)
   int prof_host = env_int("CLP_PROF_HOST", 0);      // print wall-clock marks of the scoring / solve calls (stderr)
+  int prof_laps = env_int("CLP_PROF_LAPS", 1);      // in-kernel phase timers (the split reported in clp_solution.prof_*)
+  int ll_gpu_scope = env_int("CLP_LL_GPU_SCOPE", 1);  // sharded staging: gpu-scope first look at an LL cell (system-scope polls follow)
+  int res_G_env = env_int("CLP_RES_G", 0);          // > 0: CTAs of the resident kernels (A/B runs)
+  int item_cost = env_int("CLP_ITEM_COST", (int)kItemCost);  // fixed cost of an item in the partition of the sweep (A/B runs)
   DevBuf prof_buf;
   int res_G = 0;                                    // CTAs of the resident kernels for the current matrix
   int res_NI = 0;
@@ -359,14 +364,14 @@ int res_pick_cfg(clp_handle h) {
 
 template <typename T>
 cudaError_t res_set_attrs(clp_handle h, int c, bool sharded) {
-  static bool done[2][kNumResCfgs][2][8] = {};  // [storage][configuration][sharded][device]: set once per process
-  bool& flag = done[sizeof(T) == 8 ? 1 : 0][c][sharded ? 1 : 0][h->device & 7];
-  if (flag) return cudaSuccess;
-  flag = true;
+  // [storage][configuration][sharded][device]: set once per process (handles may live on different host threads)
+  static std::atomic<bool> done[2][kNumResCfgs][2][8];
+  std::atomic<bool>& flag = done[sizeof(T) == 8 ? 1 : 0][c][sharded ? 1 : 0][h->device & 7];
+  if (flag.load(std::memory_order_acquire)) return cudaSuccess;
   // the attribute is a per-function PERMISSION shared by every handle of the process (two shards in one process ask
   // for different sizes): always the device maximum; the carve-out follows what each launch actually requests
   const int bytes = h->smem_optin;
-  return res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
+  const cudaError_t rc = res_dispatch(c, [&]<int NT, int U, int D, bool RING>() -> cudaError_t {
     if constexpr ((sizeof(T) == 8) != (NT == 512 && U == 2 && D == 2 && !RING)) return cudaErrorInvalidValue;
     else {
       cudaError_t e = cudaFuncSetAttribute(matvec_resident_kernel<T, NT, U, D, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -375,6 +380,8 @@ cudaError_t res_set_attrs(clp_handle h, int c, bool sharded) {
       return cudaFuncSetAttribute(solver_resident_kernel<T, NT, U, D, RING, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     }
   });
+  if (rc == cudaSuccess) flag.store(true, std::memory_order_release);
+  return rc;
 }
 
 ResArgs res_args(clp_handle h) {
@@ -399,12 +406,12 @@ ResArgs res_args(clp_handle h) {
   a.comm = h->comm.as<CommBlock>();
   for (int r = 0; r < kMaxPeers; ++r) { a.peer_ll[r] = h->peer_ll[r]; a.peer_comm[r] = h->peer_comm[r]; }
   a.spin_limit = (long long)h->spin_seconds * 1900000000LL;
-  a.ll_gpu_scope = env_int("CLP_LL_GPU_SCOPE", 1);
+  a.ll_gpu_scope = h->ll_gpu_scope;
   a.ring_stages = kResCfgs[h->res_cfg_eff].ring ? kResCfgs[h->res_cfg_eff].D : 0;
   res_pick_caps(h, h->res_cfg_eff, &a.pieces_cap, &a.state_cap);
   a.redll = h->res_redll.as<uint4>();
   a.prof_cta = h->prof_ctas ? h->prof_buf.as<double>() : nullptr;
-  a.prof_laps = (h->prof_ctas || env_int("CLP_PROF_LAPS", 1)) ? 1 : 0;
+  a.prof_laps = (h->prof_ctas || h->prof_laps) ? 1 : 0;
   return a;
 }
 
@@ -530,7 +537,7 @@ int build_sparse(clp_handle h, bool force, bool resident) {
     const long long by_bytes = (long long)((double)h->sp_nnz * (sizeof(T) + 2.0) / (32.0 * 1024.0));
     G = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(h->grid_cap > 0 ? std::min(h->grid_cap, h->sm_count) : h->sm_count, NI / 2),
                                                         std::max<long long>(1, by_bytes)));
-    if (env_int("CLP_RES_G", 0) > 0) G = std::max(1, std::min(env_int("CLP_RES_G", 0), std::min(h->sm_count, std::max(1, NI / 2))));
+    if (h->res_G_env > 0) G = std::max(1, std::min(h->res_G_env, std::min(h->sm_count, std::max(1, NI / 2))));
     h->res_G = G;
     h->res_cfg_eff = res_pick_cfg(h);
     CLP_CUDA(h, res_set_attrs<T>(h, h->res_cfg_eff, h->world > 1));
@@ -543,7 +550,7 @@ int build_sparse(clp_handle h, bool force, bool resident) {
   CLP_CUDA(h, h->sp_part.ensure(2 * ((size_t)G + 1) * sizeof(unsigned int)));
   sparse_partition_kernel<<<(G + 1 + 255) / 256, 256, 0, h->stream>>>(h->sp.itemptr, h->rows_pad, nseg, G, h->sp_part.as<unsigned int>(),
                                                                       h->sp_part.as<unsigned int>() + G + 1,
-                                                                      (unsigned int)env_int("CLP_ITEM_COST", (int)kItemCost));
+                                                                      (unsigned int)std::max(0, h->item_cost));
   CLP_CUDA(h, cudaGetLastError());
   h->sp.cta_first = h->sp_part.as<unsigned int>();
   h->sp.cta_chunk = h->sp.cta_first + G + 1;

@@ -74,3 +74,17 @@ def test_params_defaults_mirror_reference(built):
     assert (e.sigma, e.epsilon, e.mindist) == (0.01, 0.06, 0.0)
     q = clipperpy.invariants.PointNormalDistanceParams()
     assert (q.sigp, q.epsp, q.sign, q.epsn) == (0.5, 0.5, 0.10, 0.35)
+
+
+def test_batch_create_fails_loudly_without_gpu(built):
+    """the batch path has no CPU fallback either"""
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    import clipper_b200 as clipperpy
+    ip = clipperpy.invariants.EuclideanDistanceParams()
+    with pytest.raises(clipperpy.ClipperError):
+        clipperpy.BatchCLIPPER(clipperpy.invariants.EuclideanDistance(ip), clipperpy.Params())
+    with pytest.raises(TypeError):
+        clipperpy.BatchCLIPPER(object(), clipperpy.Params())
