@@ -186,11 +186,24 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
       __syncthreads();
     }
 
-    // ---- 2. scoring: warp per row, 128 columns per step; screening + survivor queue as in score_tile_kernel
+    // ---- 2. scoring: warp per row, 128 columns per step; screening + survivor queue as in score_tile_kernel.
+    //      A row's warp evaluates its diagonal block of 128 columns and the blocks to the right of it; an entry kept in
+    //      a block right of the diagonal block is also stored transposed (the pair functions are symmetric bit for bit:
+    //      squared differences and commutative products), so every pair outside the diagonal blocks is evaluated once
+    //      (ref clipper.cpp:31-56 fills the upper triangle and mirrors it).
     const BatchSmem bs = batch_smem_plan(ba.max_m);
     unsigned int* cnt = reinterpret_cast<unsigned int*>(smem + bs.cnt);                          // [rows_pad]
     unsigned short* queue = reinterpret_cast<unsigned short*>(smem + bs.queue) + warp * 128;
     float* tile = reinterpret_cast<float*>(smem + bs.tile) + warp * 128;
+    for (int i = tid; i < rows_pad; i += kBatchThreads) cnt[i] = 0u;
+    {
+      const float4 neutral4 = make_float4(-0.0f, -0.0f, -0.0f, -0.0f);
+      for (int i = 128 + warp; i < m; i += kBatchWarps) {  // the blocks left of the diagonal block: transposed stores only
+        const int jd = i & ~127;
+        for (int j = lane * 4; j < jd; j += 128) *reinterpret_cast<float4*>(M + (size_t)i * ld + j) = neutral4;
+      }
+    }
+    __syncthreads();
     {
       const float R = s_R;
       const double eps = ba.p1;  // epsilon (Euclidean) / epsp (PointNormal): the position-consistency bound
@@ -200,7 +213,8 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
         if (i < m) {
           const int ai0 = Ag[i], ai1 = Ag[m + i];
           const float4 f1i = F1[i], f2i = F2[i];
-          for (int j0 = 0; j0 < ld; j0 += 128) {
+          const int jdiag = i & ~127;
+          for (int j0 = jdiag; j0 < ld; j0 += 128) {
             unsigned int qn = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -241,7 +255,11 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
                 const double dot2 = __dadd_rn(__dadd_rn(__dmul_rn(e2i[3 % DD], e2j[3 % DD]), __dmul_rn(e2i[4 % DD], e2j[4 % DD])), __dmul_rn(e2i[5 % DD], e2j[5 % DD]));
                 scr = pointnormal_score(l1, l2, dot1, dot2, ba.p0, ba.p1, ba.p2, ba.p3);
               }
-              if (scr > ba.affinityeps) tile[l * 4 + e] = encode<float>(scr, true);  // ref clipper.cpp:53-55
+              if (scr > ba.affinityeps) {  // ref clipper.cpp:53-55
+                const float enc = encode<float>(scr, true);
+                tile[l * 4 + e] = enc;
+                if (j0 != jdiag) { M[(size_t)j * ld + i] = enc; atomicAdd(&cnt[j], 1u); }
+              }
             }
             __syncwarp();
             const float4 o4 = *reinterpret_cast<const float4*>(tile + lane * 4);
@@ -253,7 +271,7 @@ __global__ void __launch_bounds__(kBatchThreads, 3) batch_solve_kernel(BatchArgs
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
         }
-        if (lane == 0) cnt[i] = kept;
+        if (lane == 0 && kept) atomicAdd(&cnt[i], kept);
       }
     }
     __syncthreads();
