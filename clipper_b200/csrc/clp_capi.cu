@@ -99,6 +99,7 @@ struct clp_handle_s {
   int prof_ctas = env_int("CLP_PROF_CTAS", 0);      // print the per-CTA phase times of every resident solve (stderr)
   int prof_host = env_int("CLP_PROF_HOST", 0);      // print wall-clock marks of the scoring / solve calls (stderr)
   int prof_laps = env_int("CLP_PROF_LAPS", 1);      // in-kernel phase timers (the split reported in clp_solution.prof_*)
+  int stage_bulk = env_int("CLP_STAGE_BULK", 1);    // unsharded resident solver: trial vector staged by cp.async.bulk (0: register loads)
   int ll_gpu_scope = env_int("CLP_LL_GPU_SCOPE", 1);  // sharded staging: gpu-scope first look at an LL cell (system-scope polls follow)
   int res_G_env = env_int("CLP_RES_G", 0);          // > 0: CTAs of the resident kernels (A/B runs)
   int item_cost = env_int("CLP_ITEM_COST", (int)kItemCost);  // fixed cost of an item in the partition of the sweep (A/B runs)
@@ -412,6 +413,7 @@ ResArgs res_args(clp_handle h) {
   a.redll = h->res_redll.as<uint4>();
   a.prof_cta = h->prof_ctas ? h->prof_buf.as<double>() : nullptr;
   a.prof_laps = (h->prof_ctas || h->prof_laps) ? 1 : 0;
+  a.stage_bulk = h->stage_bulk;
   return a;
 }
 

@@ -65,6 +65,7 @@ struct ResArgs {
   uint4* redll;            // [2][G][8] per-CTA partial sums as self-validating LL cells (zeroed before the launch)
   double* prof_cta;        // nullable: [G][8] per-CTA phase times in ns (sweeps, epilogues, exchanges, staging), items, chunks
   int prof_laps;           // thread 0 of every CTA reads %globaltimer four times per evaluation (phase split in clp_solution)
+  int stage_bulk;          // unsharded solver: the candidate vector enters shared memory by cp.async.bulk (res_stage_bulk)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -100,8 +101,9 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned int parity, int* e
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory plan of a resident CTA (dynamic shared memory; the host uses the same function)
 // ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned int kStageBlocks = 8;  // sub-blocks (one mbarrier each) of a bulk-copied trial vector
 struct ResSmem {
-  unsigned int off_red, off_fin, off_wb, off_misc, off_bar, off_ring, total;
+  unsigned int off_red, off_fin, off_wb, off_misc, off_bar, off_sbar, off_ring, total;
   unsigned int stage_bytes;
   // optional on-chip tables behind the plan's minimum (capacities chosen by the host, a few KB: the more shared
   // memory a CTA takes, the less L1 is left for the streaming loads): the CTA's piece table, and per row the solver
@@ -120,6 +122,7 @@ __host__ __device__ inline ResSmem res_smem_plan(int m, int NW, int ring_stages,
   o = (o + 7u) & ~7u;
   s.off_misc = o; o += 128 + (unsigned int)NW * 8;  // per-warp: phase bits of the ring's mbarriers (persist across sweeps) | start of its stream (item, end)
   s.off_bar = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages * 8 : 0);
+  s.off_sbar = o; o += kStageBlocks * 8u;  // mbarriers of the bulk-copy staging (res_stage_bulk)
   o = (o + 127u) & ~127u;
   s.stage_bytes = res_round_bytes(U, esize);
   s.off_ring = o; o += (unsigned int)(ring_stages > 0 ? NW * ring_stages : 0) * s.stage_bytes;
@@ -295,6 +298,59 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
   }
   if (threadIdx.x == 0) vs[m] = 0.0;  // column of the padding entries
   __syncthreads();
+  double part = 0.0;                   // CTA-independent order: thread t adds entries t, t + NT, ...
+  for (int j = threadIdx.x; j < m; j += NT) part += vs[j];
+  return res_block_sum<NT>(part, red_s, fin);
+}
+
+// The same step with the copy engine: thread 0 issues the whole vector as kStageBlocks cp.async.bulk copies (SASS UBLKCP)
+// straight from the L2-resident candidate array into vs, each completing its own mbarrier; the CTA then normalises the
+// sub-blocks in place as they land.  No registers hold bytes in flight and the copies of all sub-blocks overlap the
+// arithmetic of the first ones.  The candidate array was written by other CTAs with generic stores and acquired through
+// the device-wide exchange: the issuing thread orders its async-proxy reads behind that with fence.proxy.async; every
+// thread fences its in-place generic writes against the next call's async-proxy writes the same way.  Same values and
+// the same CTA-independent summation order as res_stage (modes RS_DIV / RS_STEP, 16-byte aligned src).
+template <int NT>
+__device__ double res_stage_bulk(int mode, int m, const double* src, double z, double* vs, unsigned long long* bars,
+                                 unsigned int& phase, double* red_s, double* fin, int* errp, int rot, bool raw = false) {
+  // raw: the vector is staged as it is and nothing is summed (returns 0) -- the caller applies 1/|w| to the row results
+  const double nrm = sqrt(z);
+  const double rinv = 1.0 / nrm;
+  const bool scale = !raw && ((mode == RS_DIV) || (mode == RS_STEP && z > 0.0));
+  auto norm1 = [&](double w) { return (mode == RS_DIV) ? (w / nrm) : div_by_invariant(w, nrm, rinv); };
+  const int m2 = m & ~1;                                                   // bulk part: a multiple of 16 bytes
+  const int sb = (int)(((m2 + (int)kStageBlocks - 1) / (int)kStageBlocks + 1) & ~1);  // elements per sub-block (even)
+  const int k0 = ((rot % (int)kStageBlocks) + (int)kStageBlocks) % (int)kStageBlocks;  // CTAs start at different sub-blocks
+  __syncthreads();  // nobody still reads the previous trial vector
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll 1
+    for (int t = 0; t < (int)kStageBlocks; ++t) {
+      int k = k0 + t; if (k >= (int)kStageBlocks) k -= (int)kStageBlocks;
+      const int lo = k * sb, hi = min(lo + sb, m2);
+      const unsigned int bytes = hi > lo ? (unsigned int)(hi - lo) * 8u : 0u;
+      mbar_expect_tx(&bars[k], bytes);  // 0 bytes: the arrival alone completes the phase
+      if (bytes) bulk_g2s(vs + lo, src + lo, bytes, &bars[k]);
+    }
+    if (m & 1) { const double w = __ldcg(src + m - 1); vs[m - 1] = scale ? norm1(w) : w; }
+    vs[m] = 0.0;  // column of the padding entries
+  }
+#pragma unroll 1
+  for (int t = 0; t < (int)kStageBlocks; ++t) {
+    int k = k0 + t; if (k >= (int)kStageBlocks) k -= (int)kStageBlocks;
+    mbar_wait(&bars[k], phase & 1u, errp);
+    if (!scale) continue;
+    const int lo = k * sb, hi = min(lo + sb, m2);
+    for (int j = lo + 2 * (int)threadIdx.x; j < hi; j += 2 * NT) {
+      double2 w = *reinterpret_cast<double2*>(vs + j);
+      w.x = norm1(w.x); w.y = norm1(w.y);
+      *reinterpret_cast<double2*>(vs + j) = w;
+    }
+  }
+  phase ^= 1u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (raw) return 0.0;
   double part = 0.0;                   // CTA-independent order: thread t adds entries t, t + NT, ...
   for (int j = threadIdx.x; j < m; j += NT) part += vs[j];
   return res_block_sum<NT>(part, red_s, fin);
@@ -674,6 +730,14 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
     if (threadIdx.x < NW) reinterpret_cast<unsigned int*>(smem + plan.off_misc)[threadIdx.x] = 0u;
     fence_mbar_init();
   }
+  // bulk-copy staging of the candidate vector (one unsharded problem on the whole GPU only)
+  unsigned long long* const sbars = reinterpret_cast<unsigned long long*>(smem + plan.off_sbar);
+  unsigned int sphase = 0u;
+  const bool stage_bulk = !SHARDED && !SOLO && a.stage_bulk != 0;
+  if constexpr (!SHARDED && !SOLO) {
+    if (threadIdx.x < kStageBlocks) mbar_init(&sbars[threadIdx.x], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
 
   // piece table and per-row state (u, gradF, Mhat u, Chat u of the current and the next iterate): on chip when the
@@ -733,7 +797,7 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   double vals[kRedVals], loc[kRedVals];
   long long n_evals = 0, n_inner = 0, n_matvec = 0;
   int cur = 0, cpar = 0, red_par = 0, status = 0, i_outer = 0;
-  double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0;
+  double d = 0.0, F = 0.0, sum_cur = 0.0, z = 0.0, sw = 0.0;  // z, sw: |w|^2 and sum(w) of the candidate the next evaluation stages
   unsigned long long round = 0, seq = a.seq0;
   unsigned int ctag = 0u;  // tag under which the candidates of parity cpar were written
   unsigned long long ns_mv = 0, ns_cb = 0, ns_ex = 0, ns_st = 0, tmark = global_ns();
@@ -777,9 +841,11 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   }
   // ---- phase 1: u /= |u|; Mhat u, Chat u; initial d (clipper.cpp:198-209) ----------------------
   {
-    const double sumu = res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
-                                               SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
-                                               errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
+    const double sumu = stage_bulk
+        ? res_stage_bulk<NT>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp, z, vs, sbars, sphase, red_s, fin, errp, bid)
+        : res_stage<NT, SHARDED>(RS_DIV, m, a.cand + (size_t)(cpar * 2) * mp,
+                                 SHARDED ? a.ll + (size_t)(cpar * 2) * mp : nullptr, ctag, z, vs, red_s, fin,
+                                 errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
     RES_LAP(ns_st);
     RES_SWEEP();
     cur = 1;
@@ -810,22 +876,34 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         loc[0] += ui * g;
         double w = __dadd_rn(ui, __dmul_rn(1.0, g)); w = (w < 0.0) ? 0.0 : w;
         loc[1] += w * w;
+        loc[2] += w;
         cand_store(cpar ^ 1, 0, i, w, tag);
       }
       RES_EXCHANGE();
       cpar ^= 1; ctag = tag;
-      F = vals[0]; z = vals[1];
+      F = vals[0]; z = vals[1]; sw = vals[2];
     }
     int ckind = 0;  // which candidate of parity cpar the next evaluation tries
     for (int j = 0; j < P.maxiniters; ++j) {
       double alpha = 1.0;
-      double Fnew = 0.0, deltaF = 0.0, du2 = 0.0, zB = 0.0, sum_trial = sum_cur;
+      double Fnew = 0.0, deltaF = 0.0, du2 = 0.0, zB = 0.0, swB = 0.0, sum_trial = sum_cur;
       const int nxt = cur ^ 1;
       for (int k = 0; k < P.maxlsiters; ++k) {
         // trial point into shared memory, sweep of the CTA's rows
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
-        const double sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
-                                                   vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
+        // Bulk staging leaves the candidate w as it is in shared memory; unew = w / |w| (clipper.cpp:237) is applied to
+        // the row results instead -- M w, C w and sum(w) are linear in w -- i.e. to this CTA's ~m/G rows rather than to all
+        // m entries in every CTA (the divisions were 5 of the 7 us this step took per evaluation at m = 20 000).
+        const double nrm_l = sqrt(z), rinv_l = 1.0 / nrm_l;
+        const bool lzs = stage_bulk && z > 0.0;
+        double sumv;
+        if (stage_bulk) {
+          res_stage_bulk<NT>(RS_STEP, m, a.cand + coff, z, vs, sbars, sphase, red_s, fin, errp, bid, true);
+          sumv = lzs ? div_by_invariant(sw, nrm_l, rinv_l) : sw;
+        } else {
+          sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
+                                        vs, red_s, fin, errp, a.spin_limit, a.ll_gpu_scope, bid * 416);
+        }
         RES_LAP(ns_st);
         RES_SWEEP();
         ++n_evals;
@@ -836,7 +914,11 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
         RES_FOR_ROWS(i, itx, sx) {
           double Mv, Cv;
           res_gather_pieces(ptab, isub, ptab_sh, wmask, itx, sx, w0_, w1_, Mv, Cv);
-          const double un = vs[i];
+          double un = vs[i];
+          if (lzs) {
+            un = div_by_invariant(un, nrm_l, rinv_l);
+            Mv = div_by_invariant(Mv, nrm_l, rinv_l); Cv = div_by_invariant(Cv, nrm_l, rinv_l);
+          }
           const double g = grad_entry(un, sumv, Mv, Cv, d);
           S(R_U0 + nxt, t_, i) = un; S(R_G0 + nxt, t_, i) = g; S(R_MV0 + nxt, t_, i) = Mv; S(R_CV0 + nxt, t_, i) = Cv;
           const double uo = S(R_U0 + cur, t_, i), go = S(R_G0 + cur, t_, i);
@@ -847,24 +929,25 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
           loc[2] += wa * wa;
           double wb_ = __dadd_rn(un, __dmul_rn(1.0, g)); wb_ = (wb_ < 0.0) ? 0.0 : wb_;
           loc[3] += wb_ * wb_;
+          loc[4] += wb_; loc[5] += wa;
           cand_store(cpar ^ 1, 0, i, wb_, tag);
           cand_store(cpar ^ 1, 1, i, wa, tag);
         }
         RES_EXCHANGE();
         cpar ^= 1; ctag = tag;
         // the line-search decision (clipper.cpp:242-251), identical on every CTA / rank
-        Fnew = vals[0]; du2 = vals[1]; zB = vals[3];
+        Fnew = vals[0]; du2 = vals[1]; zB = vals[3]; swB = vals[4];
         deltaF = Fnew - F;
         sum_trial = sumv;
         if (deltaF < -P.eps) {
           alpha = alpha_rej;
-          if (k + 1 < P.maxlsiters) { z = vals[2]; ckind = 1; continue; }
+          if (k + 1 < P.maxlsiters) { z = vals[2]; sw = vals[5]; ckind = 1; continue; }
         }
         break;
       }
       // accept (also when the line search ran out, clipper.cpp:256-258)
       const double deltau = sqrt(du2);
-      F = Fnew; cur = nxt; sum_cur = sum_trial; z = zB; ckind = 0;
+      F = Fnew; cur = nxt; sum_cur = sum_trial; z = zB; sw = swB; ckind = 0;
       ++n_inner;
       if (deltau < P.tol_u || fabs(deltaF) < P.tol_F) break;
     }
