@@ -212,7 +212,8 @@ __device__ __forceinline__ void ll_ld4(const uint4* p, unsigned int& lo, unsigne
 template <int NT, bool SHARDED>
 __device__ double res_stage(int mode, int m, const double* src, const uint4* cells, unsigned int tag, double z,
                             double* vs, double* red_s, double* fin, int* errp, long long spin_limit, int ll_gpu_scope = 0,
-                            int rot = 0) {
+                            int rot = 0, bool raw = false) {
+  // raw: the vector is staged as it is and nothing is summed (returns 0) -- the caller applies 1/|w| to the row results
   // Every CTA of the grid reads the SAME m values at the same moment.  Measured on B200 (profiles/r02i): with all 148
   // CTAs walking the vector in the same order, four 8-byte loads in flight per thread, this step took 14.7 us per
   // evaluation at m = 20 000 -- a fifth of the solver -- while the sweep itself ran at the HBM peak.  So: 16-byte
@@ -220,7 +221,7 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
   // queue on the same L2 lines; the sum is then taken in a CTA-independent order from shared memory.
   const double nrm = sqrt(z);
   const double rinv = 1.0 / nrm;
-  const bool scale = (mode == RS_DIV) || (mode == RS_STEP && z > 0.0);
+  const bool scale = !raw && ((mode == RS_DIV) || (mode == RS_STEP && z > 0.0));
   const int npair = (m + 1) >> 1;
   const int K = (npair + NT - 1) / NT;          // pair slots per thread
   const int span = K * NT;
@@ -298,6 +299,7 @@ __device__ double res_stage(int mode, int m, const double* src, const uint4* cel
   }
   if (threadIdx.x == 0) vs[m] = 0.0;  // column of the padding entries
   __syncthreads();
+  if (raw) return 0.0;
   double part = 0.0;                   // CTA-independent order: thread t adds entries t, t + NT, ...
   for (int j = threadIdx.x; j < m; j += NT) part += vs[j];
   return res_block_sum<NT>(part, red_s, fin);
@@ -734,6 +736,8 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
   unsigned long long* const sbars = reinterpret_cast<unsigned long long*>(smem + plan.off_sbar);
   unsigned int sphase = 0u;
   const bool stage_bulk = !SHARDED && !SOLO && a.stage_bulk != 0;
+  // candidate staged as it is, 1/|w| applied to the row results: whenever a CTA owns fewer rows than the vector has entries
+  const bool stage_raw = !SOLO && a.stage_bulk != 0;
   if constexpr (!SHARDED && !SOLO) {
     if (threadIdx.x < kStageBlocks) mbar_init(&sbars[threadIdx.x], 1);
     fence_mbar_init();
@@ -891,14 +895,16 @@ __device__ void res_solve_body(const ResArgs& a, unsigned char* smem) {
       for (int k = 0; k < P.maxlsiters; ++k) {
         // trial point into shared memory, sweep of the CTA's rows
         const size_t coff = (size_t)(cpar * 2 + ckind) * mp;
-        // Bulk staging leaves the candidate w as it is in shared memory; unew = w / |w| (clipper.cpp:237) is applied to
+        // The candidate w is staged as it is (by the copy engine when unsharded); unew = w / |w| (clipper.cpp:237) is applied to
         // the row results instead -- M w, C w and sum(w) are linear in w -- i.e. to this CTA's ~m/G rows rather than to all
         // m entries in every CTA (the divisions were 5 of the 7 us this step took per evaluation at m = 20 000).
         const double nrm_l = sqrt(z), rinv_l = 1.0 / nrm_l;
-        const bool lzs = stage_bulk && z > 0.0;
+        const bool lzs = stage_raw && z > 0.0;
         double sumv;
-        if (stage_bulk) {
-          res_stage_bulk<NT>(RS_STEP, m, a.cand + coff, z, vs, sbars, sphase, red_s, fin, errp, bid, true);
+        if (stage_raw) {
+          if (stage_bulk) res_stage_bulk<NT>(RS_STEP, m, a.cand + coff, z, vs, sbars, sphase, red_s, fin, errp, bid, true);
+          else res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z, vs, red_s, fin, errp,
+                                      a.spin_limit, a.ll_gpu_scope, bid * 416, true);
           sumv = lzs ? div_by_invariant(sw, nrm_l, rinv_l) : sw;
         } else {
           sumv = res_stage<NT, SHARDED>(RS_STEP, m, a.cand + coff, SHARDED ? a.ll + coff : nullptr, ctag, z,
