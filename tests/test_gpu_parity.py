@@ -613,6 +613,38 @@ def test_resident_load_pipelines_agree(clp, orc, m):
             os.environ["CLP_RES_CFG"] = old
 
 
+@pytest.mark.parametrize("m", [3001])
+def test_resident_staging_paths_agree(clp, orc, m):
+    """CLP_STAGE_BULK=1 (default): the candidate enters shared memory as it is through cp.async.bulk and 1/|w| is applied
+    to the row results; 0: register loads, every entry normalised by every CTA.  Same inlier set as the oracle either
+    way, objective equal to rounding (profiles/r02s_stage_bulk_ab.txt: 5e-13 at c2).  Odd m: the last entry takes the
+    scalar path beside the 16-byte-granular bulk copies."""
+    import os
+    from clipper_b200 import datagen
+    prob = datagen.config_problem("c2", m); cfg = prob["cfg"]
+    o = orc.Oracle(); o.score_euclidean(prob["D1"], prob["D2"], prob["A"], sigma=cfg["sigma"], epsilon=cfg["epsilon"])
+    so = o.solve(prob["u0"])
+    got = []
+    old = os.environ.get("CLP_STAGE_BULK")
+    try:
+        for flag in ("1", "0"):
+            os.environ["CLP_STAGE_BULK"] = flag   # read when the handle is created
+            c = make_euclid(clp, sigma=cfg["sigma"], epsilon=cfg["epsilon"])
+            c.score_pairwise_consistency(prob["D1"], prob["D2"], prob["A"])
+            assert c.dense_mode() == 6
+            c.solve(prob["u0"]); s = c.get_solution()
+            assert sorted(s.nodes) == sorted(so.nodes.tolist())
+            assert abs(s.score - so.score) <= 1e-5 * abs(so.score)
+            got.append(s)
+    finally:
+        if old is None:
+            os.environ.pop("CLP_STAGE_BULK", None)
+        else:
+            os.environ["CLP_STAGE_BULK"] = old
+    assert got[0].nodes == got[1].nodes
+    assert abs(got[0].score - got[1].score) <= 1e-9 * abs(got[1].score)
+
+
 def test_resident_at_its_size_limit(clp, orc):
     """m = 27 648: the fp64 trial vector takes 221 KB of the 227 KB of shared memory, the on-chip epilogue tables do
     not fit any more (HBM fallback); one column more and the segmented solver takes over."""
