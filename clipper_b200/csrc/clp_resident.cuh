@@ -9,8 +9,11 @@
 // WHOLE trial vector fits the 227 KB of shared memory of an SM (m <= 27 000 in fp64), one fat CTA per SM keeps the vector
 // resident, every row is owned by exactly one CTA, and the combine step (gradient entry, objective and step-norm
 // partial sums, BOTH candidate next trial points) runs in the tail of the sweep.  Per evaluation:
-//     stage v (L2 -> shared, 8 B per column; exact division by the norm) -> sweep the CTA's rows -> per-row epilogue ->
-//     publish 8 partial sums -> one arrival counter -> every CTA adds the G x 8 table in the same fixed order.
+//     stage the candidate w (L2 -> shared, 8 B per column, as it is: eight cp.async.bulk copies with mbarrier completion
+//     when unsharded, LL cells when sharded) -> sweep the CTA's rows -> per-row epilogue (unew = w / |w| is linear, so
+//     the exact division by the norm is applied to the row's M w, C w and to sum(w) instead of to every entry of the
+//     vector in every CTA) -> publish 8 partial sums -> one arrival counter -> every CTA adds the G x 8 table in the
+//     same fixed order.
 // No partial table in HBM, no last-arriver serial reduction, no release hop.
 //
 // Layout: the compact sliced-ELL copy of clp_sparse.cuh with ONE segment = the whole row (16-bit column INDEX per
